@@ -1,0 +1,146 @@
+/*
+ * mcp_b200.h -- C ABI of the B200-native Monte-Carlo hot path (libmcp_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of bcosm/MonteCarloOptionsPricer: normal generation ->
+ * GBM / rough-volatility path simulation -> Longstaff-Schwartz backward induction + payoff averaging.
+ * Everything behind these entry points is hand-written CUDA for sm_100a; there is no CPU fallback: every
+ * call fails with MCP_ERR_CUDA when no device is usable.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repository):
+ *   mcp_gen_rbergomi            RoughVolatility::GenerateStockPricePaths   include/models/RoughVolatility.h:15-19
+ *                               (body src/models/RoughVolatility.cpp:312-368, fGn :212-309)
+ *   mcp_gen_gbm                 [new] constant-variance special case of the same recursion (:354-364)
+ *   mcp_pathset_upload_*        the `const std::vector<std::vector<double>>& pricePaths` argument that
+ *                               every pricer takes (include/models/LSMPricer.h:8-14 and siblings)
+ *   mcp_lsm_price               LSM::PredictOptionPrice                     include/models/LSMPricer.h:8-14
+ *                               (body src/models/LSMPricer.cpp:19-102)
+ *   mcp_lsm_price_host_rows     the same call, bound directly to host rows  src/core/PredictionGen.cpp:790
+ *
+ * Conventions: plain pointers and sizes only; caller allocates every output; no ownership transfer; no
+ * exceptions cross the boundary; every function returns an int status (0 = ok, negative = error class) and
+ * the message is available from mcp_last_error(ctx).  A ctx is NOT thread-safe: use one per host thread
+ * (the reference instantiates its pricers per OpenMP thread, src/core/PredictionGen.cpp:566-570).
+ */
+#ifndef MCP_B200_H
+#define MCP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCP_B200_ABI_VERSION 1
+
+typedef struct mcp_ctx mcp_ctx;         /* engine handle: device, stream, workspaces, optional NCCL communicator */
+typedef struct mcp_pathset mcp_pathset; /* device-resident TIME-MAJOR slab  S[(n_steps+1)][ld]  (ld >= n_paths) */
+
+enum mcp_status {
+    MCP_OK = 0,
+    MCP_ERR_INVALID = -1,     /* bad argument */
+    MCP_ERR_CUDA = -2,        /* CUDA runtime / no device / kernel failure */
+    MCP_ERR_NCCL = -3,        /* NCCL missing or failed */
+    MCP_ERR_NOMEM = -4,       /* device or host allocation failed */
+    MCP_ERR_EMPTY_PATHS = -5, /* the reference's "Empty pricePaths." std::runtime_error (LSMPricer.cpp:28-30) */
+    MCP_ERR_UNSUPPORTED = -6, /* valid request outside the implemented envelope (e.g. poly_order > 6) */
+    MCP_ERR_DOMAIN = -7       /* the reference would throw a domain error (e.g. sigma <= 0, strike <= 0) */
+};
+
+enum mcp_dtype { MCP_F32 = 0, MCP_F64 = 1 };       /* storage type of a path slab / of the LSM carry */
+enum mcp_basis { MCP_BASIS_MONOMIAL = 0,           /* 1, S, S^2 ... (LSMPricer.cpp:9-17) */
+                 MCP_BASIS_LAGUERRE = 1 };         /* L_0..L_p(S/K), unweighted: spans the same space */
+
+/* ------------------------------------------------------------------------------------------- engine */
+int mcp_abi_version(void);
+int mcp_create(int device, mcp_ctx **out);
+int mcp_destroy(mcp_ctx *ctx);
+const char *mcp_last_error(const mcp_ctx *ctx); /* ctx may be NULL: error of the last failed mcp_create */
+int mcp_set_stream(mcp_ctx *ctx, void *cuda_stream); /* run on a caller-owned cudaStream_t (NULL = own stream) */
+int mcp_synchronize(mcp_ctx *ctx);
+int mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *free_bytes,
+                    size_t *total_bytes);
+uint64_t mcp_launch_count(const mcp_ctx *ctx);  /* kernels launched by this ctx since creation */
+
+/* ---------------------------------------------------------------------------------------- multi-GPU
+ * Paths shard across ranks (global path id = path_offset + local id); the only exchanged data are the
+ * per-step regression moments and the final sums (NCCL all-reduce, fp64).  One ctx per rank/GPU. */
+int mcp_comm_unique_id(void *id128);                                  /* rank 0: 128-byte ncclUniqueId */
+int mcp_comm_init(mcp_ctx *ctx, int rank, int nranks, const void *id128);
+int mcp_comm_info(const mcp_ctx *ctx, int *rank, int *nranks);
+
+/* ----------------------------------------------------------------------------------------- pathsets */
+int mcp_pathset_create(mcp_ctx *ctx, int64_t n_paths, int n_steps, int dtype, mcp_pathset **out);
+int mcp_pathset_destroy(mcp_pathset *ps);
+int mcp_pathset_info(const mcp_pathset *ps, int64_t *n_paths, int *n_steps, int64_t *ld, int *dtype,
+                     void **device_ptr);
+/* host [path][step] (the reference's layout), row stride `ld_host` elements, n_steps+1 columns used */
+int mcp_pathset_upload_f64(mcp_pathset *ps, const double *host, int64_t ld_host);
+int mcp_pathset_upload_rows_f64(mcp_pathset *ps, const double *const *rows); /* vector<vector<double>> rows */
+int mcp_pathset_download_f64(const mcp_pathset *ps, double *host, int64_t ld_host);
+/* exact device values, time-major [step][path] */
+int mcp_pathset_download_timemajor_f32(const mcp_pathset *ps, float *host, int64_t ld_host);
+
+/* --------------------------------------------------------------------------------------- generators */
+typedef struct mcp_rbergomi_params {
+    double S0, r, xi, H, eta, rho, dt;
+} mcp_rbergomi_params;
+
+typedef struct mcp_gbm_params {
+    double S0, r, sigma, dt;
+} mcp_gbm_params;
+
+/* Fills ps (n_steps, n_paths from the pathset).  Normals: native Philox4x32-10 streams keyed by `seed`
+ * and the GLOBAL path id (path_offset + i), or, when `injected` != NULL, host floats in the reference's
+ * consumption order: rbergomi [n_paths][4n] = Zre0,Zim0,..,Zre(n-1),Zim(n-1),W1[0..n),W2[0..n)
+ * (RoughVolatility.cpp:346-352); gbm [n_paths][n].  `dump` (nullable, same layout) receives the normals
+ * actually used, so a native-Philox run can be replayed through the CPU oracle. */
+int mcp_gen_rbergomi(mcp_ctx *ctx, mcp_pathset *ps, const mcp_rbergomi_params *p, uint64_t seed,
+                     uint64_t path_offset, const float *injected, float *dump);
+int mcp_gen_gbm(mcp_ctx *ctx, mcp_pathset *ps, const mcp_gbm_params *p, uint64_t seed, uint64_t path_offset,
+                const float *injected, float *dump);
+/* Raw generator words, for known-answer tests: out[4*i..4*i+3] = Philox4x32-10(ctr=(i_lo,i_hi,c2,c3), key=seed) */
+int mcp_philox_raw(mcp_ctx *ctx, uint64_t seed, uint64_t first, int64_t count, uint32_t c2, uint32_t c3,
+                   uint32_t *out_host);
+
+/* ---------------------------------------------------------------------------------------------- LSM */
+typedef struct mcp_lsm_params {
+    double r, strike, maturity, dt;
+    int is_call;
+    int poly_order; /* 0..6 */
+    int basis;      /* mcp_basis: affects only the coefficient table that is returned */
+    int carry;      /* mcp_dtype of the value carry V: MCP_F64 = parity mode, MCP_F32 = throughput mode */
+} mcp_lsm_params;
+
+typedef struct mcp_lsm_result {
+    double price;      /* mean_i V[i][0]                              (LSMPricer.cpp:97-101) */
+    double std_error;  /* [new] sample std of V[:,0] / sqrt(N)        */
+    double sum_v0, sum_sq_dev; /* sum_i V0_i and sum_i (V0_i - mean)^2 over ALL ranks */
+    int64_t n_paths_global;
+    float elapsed_ms;  /* device time of the sweep (CUDA events on the ctx stream) */
+    int n_kernel_launches;
+} mcp_lsm_result;
+
+/* coeffs (nullable): host [n_steps][poly_order+1], row j = regression at step j in the requested basis,
+ *                    zeros where no path was in the money / past maturity;
+ * first_exercise (nullable): host int32 [n_paths], tau_i = min{ j : exercised } else n_steps;
+ * v0 (nullable): host double [n_paths], V[i][0]. */
+int mcp_lsm_price(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *p, mcp_lsm_result *res,
+                  double *coeffs, int32_t *first_exercise, double *v0);
+
+/* One call = LSM::PredictOptionPrice(pricePaths, r, strike, maturity, dt, isCall, polyOrder): uploads
+ * n_paths host rows of n_cols doubles (kept in fp64 on the device), prices, returns the mean. */
+int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_paths, int n_cols, double r,
+                            double strike, double maturity, double dt, int is_call, int poly_order,
+                            double *price);
+
+/* One call = generate (native Philox) + LSM on the device, nothing but parameters in and a result out.
+ * n_paths is THIS rank's share; with a communicator the regression and the mean are global. */
+int mcp_price_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *model, const mcp_lsm_params *lsm,
+                           int64_t n_paths, int n_steps, uint64_t seed, uint64_t path_offset,
+                           mcp_lsm_result *res, float *gen_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCP_B200_H */

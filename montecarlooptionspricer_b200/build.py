@@ -1,0 +1,81 @@
+"""Build the in-tree native libraries with explicit nvcc / g++ commands (sm_100a only).
+
+  montecarlooptionspricer_b200/libmcp_b200.so          CUDA kernels + the C ABI (include/mcp_b200.h)
+  montecarlooptionspricer_b200/libmcp_b200_plugins.so  C++ host plugin classes with the reference's signatures
+
+Run `python -m montecarlooptionspricer_b200.build` (or `__graft_entry__.build()`).  nvcc cross-compiles without a
+GPU; the built .so files are git-ignored but travel to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+HOST = os.path.join(PKG, "host")
+LIB = os.path.join(PKG, "libmcp_b200.so")
+PLUGINS = os.path.join(PKG, "libmcp_b200_plugins.so")
+
+CU_SOURCES = ["ctx.cu", "pathset.cu", "gen_rbergomi.cu", "gen_gbm.cu", "lsm.cu", "pricers.cu", "estimators.cu"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
+        os.path.join(ROOT, "include", "mcp_b200.h")]
+    if not force and _newer(LIB, deps):
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-ldl"]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.run(cmd, check=True, env=env, cwd=CSRC)
+    return LIB
+
+
+def build_plugins(force: bool = False) -> str:
+    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")] if os.path.isdir(HOST) else []
+    if not srcs:
+        return ""
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".h", ".hpp"))] + [LIB]
+    if not force and _newer(PLUGINS, deps):
+        return PLUGINS
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST] + srcs + [
+        "-o", PLUGINS, "-L", PKG, "-lmcp_b200", "-Wl,-rpath,$ORIGIN"]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.run(cmd, check=True, env=env)
+    return PLUGINS
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force=force, verbose=verbose)
+    build_plugins(force=force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

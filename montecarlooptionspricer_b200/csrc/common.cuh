@@ -1,0 +1,81 @@
+// common.cuh -- shared host-side plumbing for libmcp_b200.so (engine handle, pathset, error handling).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mcp_b200.h"
+
+struct McpNccl;  // dlopen'ed NCCL entry points (ctx.cu)
+
+// One engine handle per host thread / per GPU rank.
+struct mcp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // == own_stream unless mcp_set_stream installed a caller stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // multi-GPU
+    void* comm = nullptr;  // ncclComm_t
+    int rank = 0, nranks = 1;
+
+    // grow-only device scratch (regression partials, coefficient tables, transposition staging ...)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // grow-only pinned host staging
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // grow-only LSM carry buffer (kept across calls so repeated pricing does not re-allocate)
+    void* carry = nullptr;
+    size_t carry_bytes = 0;
+    // cached pathset for mcp_price_rbergomi_lsm
+    mcp_pathset* cached_ps = nullptr;
+};
+
+struct mcp_pathset {
+    mcp_ctx* ctx = nullptr;
+    int64_t n_paths = 0;
+    int n_steps = 0;   // slab has n_steps+1 rows
+    int64_t ld = 0;    // row stride in elements (n_paths rounded up to 128)
+    int dtype = MCP_F32;
+    void* data = nullptr;
+    size_t bytes = 0;
+};
+
+int mcp_fail(mcp_ctx* ctx, int code, const char* fmt, ...);
+int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes);
+int mcp_pinned_reserve(mcp_ctx* ctx, size_t bytes);
+int mcp_carry_reserve(mcp_ctx* ctx, size_t bytes);
+// all-reduce (sum, fp64) of a device buffer on ctx->stream; no-op without a communicator
+int mcp_allreduce_f64(mcp_ctx* ctx, double* dev, int count);
+
+#define MCP_CUDA(ctx, call)                                                                            \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return mcp_fail((ctx), MCP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define MCP_LAUNCH_CHECK(ctx)                                                                          \
+    do {                                                                                               \
+        (ctx)->launches++;                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                                          \
+        if (e__ != cudaSuccess)                                                                        \
+            return mcp_fail((ctx), MCP_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                   \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                              \
+    } while (0)
+
+#define MCP_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != MCP_OK) return rc__; \
+    } while (0)
+
+static inline int64_t mcp_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

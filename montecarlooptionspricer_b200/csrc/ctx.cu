@@ -1,0 +1,224 @@
+// ctx.cu -- engine handle, error reporting, workspaces, and the NCCL doorway (dlopen'ed so that the same
+// libmcp_b200.so works inside a torch process -- which already maps its own libnccl.so.2 -- and from plain
+// C++ hosts against the system NCCL).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local std::string g_create_err;
+
+int mcp_fail(mcp_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------- NCCL
+typedef struct { char internal[128]; } mcp_nccl_uid;
+struct McpNccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(mcp_nccl_uid*) = nullptr;
+    int (*CommInitRank)(void**, int, mcp_nccl_uid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static McpNccl g_nccl;
+
+static bool nccl_load(std::string* why) {
+    if (g_nccl.ok) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { *why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(mcp_nccl_uid*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, mcp_nccl_uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        *why = "NCCL symbols missing";
+        return false;
+    }
+    g_nccl.ok = true;
+    return true;
+}
+
+int mcp_allreduce_f64(mcp_ctx* ctx, double* dev, int count) {
+    if (!ctx->comm || ctx->nranks <= 1) return MCP_OK;
+    const int ncclFloat64 = 8, ncclSum = 0;
+    int rc = g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+    if (rc != 0)
+        return mcp_fail(ctx, MCP_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return MCP_OK;
+}
+
+extern "C" {
+
+int mcp_abi_version(void) { return MCP_B200_ABI_VERSION; }
+
+int mcp_create(int device, mcp_ctx** out) {
+    if (!out) return mcp_fail(nullptr, MCP_ERR_INVALID, "mcp_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return mcp_fail(nullptr, MCP_ERR_CUDA, "mcp_create: no CUDA device (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return mcp_fail(nullptr, MCP_ERR_INVALID, "mcp_create: device %d out of range [0,%d)", device, ndev);
+    mcp_ctx* ctx = new mcp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete ctx;
+        return mcp_fail(nullptr, MCP_ERR_CUDA, "mcp_create: %s", cudaGetErrorString(e));
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    if (prop.major != 10) {
+        delete ctx;
+        return mcp_fail(nullptr, MCP_ERR_CUDA, "mcp_create: device is sm_%d%d; this library ships sm_100a code only", prop.major, prop.minor);
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        delete ctx;
+        return mcp_fail(nullptr, MCP_ERR_CUDA, "mcp_create: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return MCP_OK;
+}
+
+int mcp_destroy(mcp_ctx* ctx) {
+    if (!ctx) return MCP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->cached_ps) mcp_pathset_destroy(ctx->cached_ps);
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->carry) cudaFree(ctx->carry);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MCP_OK;
+}
+
+const char* mcp_last_error(const mcp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mcp_set_stream(mcp_ctx* ctx, void* s) {
+    if (!ctx) return MCP_ERR_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return MCP_OK;
+}
+
+int mcp_synchronize(mcp_ctx* ctx) {
+    if (!ctx) return MCP_ERR_INVALID;
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCP_OK;
+}
+
+int mcp_device_info(mcp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_b, size_t* total_b) {
+    if (!ctx) return MCP_ERR_INVALID;
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    size_t f = 0, t = 0;
+    MCP_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (free_b) *free_b = f;
+    if (total_b) *total_b = t;
+    return MCP_OK;
+}
+
+uint64_t mcp_launch_count(const mcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mcp_comm_unique_id(void* id128) {
+    std::string why;
+    if (!id128) return MCP_ERR_INVALID;
+    if (!nccl_load(&why)) return mcp_fail(nullptr, MCP_ERR_NCCL, "%s", why.c_str());
+    mcp_nccl_uid uid;
+    int rc = g_nccl.GetUniqueId(&uid);
+    if (rc != 0) return mcp_fail(nullptr, MCP_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+    memcpy(id128, &uid, 128);
+    return MCP_OK;
+}
+
+int mcp_comm_init(mcp_ctx* ctx, int rank, int nranks, const void* id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return mcp_fail(ctx, MCP_ERR_INVALID, "mcp_comm_init: bad arguments");
+    std::string why;
+    if (!nccl_load(&why)) return mcp_fail(ctx, MCP_ERR_NCCL, "%s", why.c_str());
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    mcp_nccl_uid uid;
+    memcpy(&uid, id128, 128);
+    void* comm = nullptr;
+    int rc = g_nccl.CommInitRank(&comm, nranks, uid, rank);
+    if (rc != 0) return mcp_fail(ctx, MCP_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return MCP_OK;
+}
+
+int mcp_comm_info(const mcp_ctx* ctx, int* rank, int* nranks) {
+    if (!ctx) return MCP_ERR_INVALID;
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    return MCP_OK;
+}
+
+}  // extern "C"
+
+int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return MCP_OK;
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    if (cudaMalloc(&ctx->scratch, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return mcp_fail(ctx, MCP_ERR_NOMEM, "device scratch allocation of %zu bytes failed", bytes);
+    }
+    ctx->scratch_bytes = bytes;
+    return MCP_OK;
+}
+
+int mcp_carry_reserve(mcp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->carry_bytes) return MCP_OK;
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->carry) cudaFree(ctx->carry);
+    ctx->carry = nullptr;
+    ctx->carry_bytes = 0;
+    if (cudaMalloc(&ctx->carry, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return mcp_fail(ctx, MCP_ERR_NOMEM, "device carry allocation of %zu bytes failed", bytes);
+    }
+    ctx->carry_bytes = bytes;
+    return MCP_OK;
+}
+
+int mcp_pinned_reserve(mcp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return MCP_OK;
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    if (cudaMallocHost(&ctx->pinned, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return mcp_fail(ctx, MCP_ERR_NOMEM, "pinned host allocation of %zu bytes failed", bytes);
+    }
+    ctx->pinned_bytes = bytes;
+    return MCP_OK;
+}

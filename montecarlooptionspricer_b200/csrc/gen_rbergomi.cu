@@ -1,0 +1,413 @@
+// gen_rbergomi.cu -- rough-volatility (spectral "fGn") price paths, written time-major into HBM.
+//
+// Replaces RoughVolatility::GenerateStockPricePaths' hot loop (src/models/RoughVolatility.cpp:346-365):
+//   Z_k complex normals                       :347 (genComplexGaussians :238-250)
+//   A = phi (.) Z, zero-pad, DFT-, /M'        :348 (fractionalGaussian :264-292, fft :171-202)
+//   X = sqrt(2H) eta Re(A)                    :284-291
+//   v = xi exp(X - eta^2 t^{2H} / 2)          :349 (forwardVariance :294-309)
+//   S_j = S_{j-1} exp((r - v/2) dt + sqrt(max(0,v)) sqrt(dt) (rho W1 + sqrt(1-rho^2) W2))   :354-364
+//
+// B200 design (not a translation of the serial per-path loop):
+//   * one CTA owns a tile of TP consecutive paths; lane <-> path, so every shared-memory access of the
+//     batched FFT is bank-conflict free, every twiddle / phi / compensator operand is warp-uniform, and every
+//     global store is one full 128 B line of consecutive paths at one time index (time-major slab);
+//   * normals come from Philox4x32-10 keyed by (global path id, step): one call = the four normals a
+//     path-step consumes (Zre, Zim, W1, W2) -- nothing is carried between steps or paths;
+//   * the M'-point complex DFT runs in shared memory as radix-8 (+ one radix-4/2) decimation-in-frequency
+//     passes; output is left digit-reversed and read back through a position table, so there is no
+//     reordering pass.  sqrt(2H) eta / M' and log2(e) are folded into the phi table on the host;
+//   * the price recursion is a log-space prefix sum: per-thread serial chunk + one cross-chunk offset, then
+//     S = S0 exp2(.).  fp32 throughout: measured |rel err| vs the fp64 oracle ~3e-7 (tolerance 1e-5).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "transpose.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace {
+
+constexpr int NT = 256;  // threads per CTA
+
+struct RbParams {
+    float S0, xi, r_dt, half_dt, sq_dt, rho, rho_c;  // r*dt, 0.5*dt, sqrt(dt), rho, sqrt(1-rho^2)
+    int n;        // steps
+    int Mp;       // DFT length = nextPow2(n)
+    int n_stage;  // DIF stages
+    int radix[4];
+    int64_t n_paths, ld;
+    uint64_t path_offset;
+    int64_t ld_draws;  // row stride of the slot-major draw tables
+};
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// forward (e^{-i theta}) 4-point DFT in place
+__device__ __forceinline__ void dft4(float2& c0, float2& c1, float2& c2, float2& c3) {
+    const float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), o0 = cadd(c1, c3), o1 = mul_mi(csub(c1, c3));
+    c0 = cadd(e0, o0);
+    c2 = csub(e0, o0);
+    c1 = cadd(e1, o1);
+    c3 = csub(e1, o1);
+}
+
+// forward 8-point DFT: y[s] = sum_q x[q] w8^{qs}; result returned in natural order in x[]
+__device__ __forceinline__ void dft8(float2 (&x)[8]) {
+    const float h = 0.70710678118654752f;
+    float2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
+    float2 b0 = csub(x[0], x[4]), b1 = csub(x[1], x[5]), b2 = csub(x[2], x[6]), b3 = csub(x[3], x[7]);
+    b1 = make_float2((b1.x + b1.y) * h, (b1.y - b1.x) * h);    // * w8
+    b2 = mul_mi(b2);                                           // * w8^2
+    b3 = make_float2((b3.y - b3.x) * h, -(b3.x + b3.y) * h);   // * w8^3
+    dft4(a0, a1, a2, a3);  // even outputs 0,2,4,6
+    dft4(b0, b1, b2, b3);  // odd outputs 1,3,5,7
+    x[0] = a0; x[2] = a1; x[4] = a2; x[6] = a3;
+    x[1] = b0; x[3] = b1; x[5] = b2; x[7] = b3;
+}
+
+// One DIF pass of radix R over sub-transforms of length L, for the TP paths of the tile.
+//   inputs  x_q = A[base + q*L/R],  outputs  y_s * w_L^{j s}  back to A[base + s*L/R]
+template <int R, int TP>
+__device__ __forceinline__ void dif_pass(float2* __restrict__ A, const float2* __restrict__ tw, int Mp, int L, int g, int p) {
+    constexpr int G = NT / TP;
+    const int stride = L / R;
+    const int tw_step = Mp / L;
+    for (int bf = g; bf < Mp / R; bf += G) {
+        const int blk = bf / stride, j = bf - blk * stride;
+        float2* a = A + (size_t)(blk * L + j) * TP + p;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = a[(size_t)q * stride * TP];
+        if constexpr (R == 8) {
+            dft8(x);
+        } else if constexpr (R == 4) {
+            dft4(x[0], x[1], x[2], x[3]);
+        } else {
+            const float2 u = x[0];
+            x[0] = cadd(u, x[1]);
+            x[1] = csub(u, x[1]);
+        }
+        if (stride > 1) {
+#pragma unroll
+            for (int s = 1; s < R; ++s) x[s] = cmul(x[s], tw[(j * s * tw_step) & (Mp - 1)]);
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) a[(size_t)s * stride * TP] = x[s];
+    }
+}
+
+// Dynamic shared memory carve-up (per CTA):
+//   float2 A[Mp][TP] | float W[Mp][TP] | float tot[G][TP] | float2 phis[Mp] | float2 tw[Mp] | float comp2[Mp] | int pos[Mp]
+template <int TP, bool INJECT, bool DUMP>
+__global__ void __launch_bounds__(NT) rbergomi_paths_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
+                                                           const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
+                                                           const int* __restrict__ g_pos, const float* __restrict__ draws_in,
+                                                           float* __restrict__ draws_out, float* __restrict__ out) {
+    constexpr int G = NT / TP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Mp = P.Mp, n = P.n;
+    float2* A = reinterpret_cast<float2*>(smem_raw);
+    float* W = reinterpret_cast<float*>(A + (size_t)Mp * TP);
+    float* tot = W + (size_t)Mp * TP;
+    float2* phis = reinterpret_cast<float2*>(tot + G * TP);
+    float2* tw = phis + Mp;
+    float* comp2 = reinterpret_cast<float*>(tw + Mp);
+    int* pos = reinterpret_cast<int*>(comp2 + Mp);
+
+    const int tid = threadIdx.x, p = tid % TP, g = tid / TP;
+    for (int i = tid; i < Mp; i += NT) {
+        phis[i] = i < n ? g_phis[i] : make_float2(0.f, 0.f);
+        tw[i] = g_tw[i];
+        comp2[i] = i < n ? g_comp2[i] : 0.f;
+        pos[i] = g_pos[i];
+    }
+    const int CH = Mp >= G ? Mp / G : 1;  // contiguous time chunk owned by this thread
+    const int k0 = g * CH, k1 = min(k0 + CH, Mp);
+    const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t path = tile * TP + p;  // local path index in this slab
+        const bool live = path < P.n_paths;
+        const uint64_t gid = P.path_offset + (uint64_t)path;
+        const uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32);
+
+        // ---- phase 1: normals -> A = phis (.) Z (zero padded), W = rho W1 + rho_c W2 ------------------
+        if (g * CH < Mp) {
+#pragma unroll 2
+            for (int k = k0; k < k1; ++k) {
+                float2 a = make_float2(0.f, 0.f);
+                float w = 0.f;
+                if (k < n) {
+                    float zr, zi, w1, w2;
+                    if (INJECT) {
+                        const int64_t col = live ? path : 0;
+                        zr = draws_in[(int64_t)(2 * k) * P.ld_draws + col];
+                        zi = draws_in[(int64_t)(2 * k + 1) * P.ld_draws + col];
+                        w1 = draws_in[(int64_t)(2 * n + k) * P.ld_draws + col];
+                        w2 = draws_in[(int64_t)(3 * n + k) * P.ld_draws + col];
+                    } else {
+                        const uint4 x = philox4x32_10(c0, c1, (uint32_t)k, 0u, K);
+                        box_muller(x.x, x.y, zr, zi);
+                        box_muller(x.z, x.w, w1, w2);
+                    }
+                    if (DUMP && live) {
+                        draws_out[(int64_t)(2 * k) * P.ld_draws + path] = zr;
+                        draws_out[(int64_t)(2 * k + 1) * P.ld_draws + path] = zi;
+                        draws_out[(int64_t)(2 * n + k) * P.ld_draws + path] = w1;
+                        draws_out[(int64_t)(3 * n + k) * P.ld_draws + path] = w2;
+                    }
+                    a = cmul(phis[k], make_float2(zr, zi));
+                    w = P.rho * w1 + P.rho_c * w2;
+                }
+                A[(size_t)k * TP + p] = a;
+                W[(size_t)k * TP + p] = w;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: M'-point forward DFT in shared memory (digit-reversed output) -------------------
+        {
+            int L = Mp;
+            for (int s = 0; s < P.n_stage; ++s) {
+                const int R = P.radix[s];
+                if (R == 8) dif_pass<8, TP>(A, tw, Mp, L, g, p);
+                else if (R == 4) dif_pass<4, TP>(A, tw, Mp, L, g, p);
+                else dif_pass<2, TP>(A, tw, Mp, L, g, p);
+                L /= R;
+                __syncthreads();
+            }
+        }
+
+        // ---- phase 3: variance, log-increments, chunk-local prefix sum --------------------------------
+        float run = 0.f;
+        if (g * CH < Mp) {
+            for (int k = k0; k < k1; ++k) {
+                if (k < n) {
+                    const float X2 = A[(size_t)pos[k] * TP + p].x;             // log2(e) * X_k
+                    const float v = P.xi * fast_ex2(X2 + comp2[k]);            // xi exp(X - eta^2 t^2H / 2)
+                    const float d = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * W[(size_t)k * TP + p];
+                    run += d;
+                    W[(size_t)k * TP + p] = run;
+                }
+            }
+        }
+        tot[g * TP + p] = run;
+        __syncthreads();
+        float off = 0.f;
+        for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
+        if (live) {
+            if (g == 0) out[path] = P.S0;
+            if (g * CH < Mp) {
+                for (int k = k0; k < k1; ++k)
+                    if (k < n) out[(int64_t)(k + 1) * P.ld + path] = P.S0 * fast_ex2(1.4426950408889634f * (off + W[(size_t)k * TP + p]));
+            }
+        }
+        __syncthreads();  // A / W / tot are rewritten by the next tile
+    }
+}
+
+size_t smem_bytes(int Mp, int TP) {
+    const int G = NT / TP;
+    return (size_t)Mp * TP * 8 + (size_t)Mp * TP * 4 + (size_t)G * TP * 4 + (size_t)Mp * (8 + 8 + 4 + 4);
+}
+
+int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+template <int TP>
+int launch_tp(mcp_ctx* ctx, const RbParams& P, const PhiloxKeys& K, const float2* phis, const float2* tw, const float* comp2,
+              const int* pos, const float* din, float* dout, float* out) {
+    const size_t smem = smem_bytes(P.Mp, TP);
+    const bool inject = din != nullptr, dump = dout != nullptr;
+    void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const int*, const float*, float*, float*);
+    if (inject) kern = dump ? rbergomi_paths_kernel<TP, true, true> : rbergomi_paths_kernel<TP, true, false>;
+    else kern = dump ? rbergomi_paths_kernel<TP, false, true> : rbergomi_paths_kernel<TP, false, false>;
+    MCP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: kernel does not fit (smem %zu)", smem);
+    const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
+    int64_t grid = (int64_t)ctx->sm_count * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, NT, smem, ctx->stream>>>(P, K, phis, tw, comp2, pos, din, dout, out);
+    MCP_LAUNCH_CHECK(ctx);
+    return MCP_OK;
+}
+
+}  // namespace
+
+// Host-side tables, all in double then rounded once to fp32.
+//   phi = DFT+(zero-pad(0.5 t^{2H}) to M = nextPow2(n+1))           RoughVolatility.cpp:212-236
+//   phis_k = phi_k * sqrt(2H) eta / M' * log2(e)                    (:270 pads to M' = nextPow2(n); :284 scale; :198-200 1/M')
+//   comp2_k = -0.5 eta^2 t_k^{2H} * log2(e)                         :304
+int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<float>& phis, std::vector<float>& tw,
+                        std::vector<float>& comp2, std::vector<int>& pos, int* Mp_out, int radix[4], int* n_stage) {
+    const int M = next_pow2(n + 1), Mp = next_pow2(n);
+    const double log2e = 1.4426950408889634074;
+    std::vector<double> lam(n + 1);
+    for (int i = 0; i <= n; ++i) lam[i] = 0.5 * pow((double)i * dt, 2.0 * H);
+    const double scale = sqrt(2.0 * H) * eta / (double)Mp * log2e;
+    phis.assign((size_t)2 * Mp, 0.f);
+    for (int k = 0; k < n; ++k) {
+        double re = 0.0, im = 0.0;
+        for (int i = 0; i <= n; ++i) {
+            const long idx = ((long)k * i) % M;
+            const double ang = 2.0 * M_PI * (double)idx / (double)M;
+            re += lam[i] * cos(ang);
+            im += lam[i] * sin(ang);
+        }
+        phis[2 * k] = (float)(re * scale);
+        phis[2 * k + 1] = (float)(im * scale);
+    }
+    tw.assign((size_t)2 * Mp, 0.f);
+    for (int q = 0; q < Mp; ++q) {
+        const double ang = -2.0 * M_PI * (double)q / (double)Mp;
+        tw[2 * q] = (float)cos(ang);
+        tw[2 * q + 1] = (float)sin(ang);
+    }
+    comp2.assign((size_t)Mp, 0.f);
+    for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * pow((double)k * dt, 2.0 * H) * log2e);
+    int lg = 0;
+    while ((1 << lg) < Mp) ++lg;
+    int ns = 0, rem = lg;
+    while (rem >= 3) { radix[ns++] = 8; rem -= 3; }
+    if (rem == 2) radix[ns++] = 4;
+    if (rem == 1) radix[ns++] = 2;
+    for (int s = ns; s < 4; ++s) radix[s] = 1;
+    *n_stage = ns;
+    // position of output m after the DIF passes: m = s1 + R1 (s2 + R2 (s3 ...)),  pos = s1 Mp/R1 + s2 Mp/(R1 R2) + ...
+    pos.assign((size_t)Mp, 0);
+    for (int m = 0; m < Mp; ++m) {
+        int rest = m, L = Mp, q = 0;
+        for (int s = 0; s < ns; ++s) {
+            const int R = radix[s];
+            L /= R;
+            q += (rest % R) * L;
+            rest /= R;
+        }
+        pos[m] = q;
+    }
+    *Mp_out = Mp;
+    return 0;
+}
+
+extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergomi_params* prm, uint64_t seed, uint64_t path_offset,
+                                const float* injected, float* dump) {
+    if (!ctx || !ps || !prm) return MCP_ERR_INVALID;
+    if (ps->ctx != ctx) return mcp_fail(ctx, MCP_ERR_INVALID, "rbergomi: pathset belongs to another ctx");
+    if (ps->dtype != MCP_F32) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: generators write fp32 slabs");
+    const int n = ps->n_steps;
+    if (n < 1) return mcp_fail(ctx, MCP_ERR_INVALID, "rbergomi: n_steps must be >= 1");
+    if (n > 4096) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n_steps %d > 4096", n);
+    if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || fabs(prm->rho) > 1.0)
+        return mcp_fail(ctx, MCP_ERR_DOMAIN, "rbergomi: need dt > 0, H >= 0, |rho| <= 1");
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (injected && dump) {  // the normals used ARE the injected ones
+        memcpy(dump, injected, (size_t)ps->n_paths * 4 * n * sizeof(float));
+        dump = nullptr;
+    }
+
+    std::vector<float> phis, tw, comp2;
+    std::vector<int> pos;
+    RbParams P;
+    memset(&P, 0, sizeof(P));
+    mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, phis, tw, comp2, pos, &P.Mp, P.radix, &P.n_stage);
+    P.S0 = (float)prm->S0;
+    P.xi = (float)prm->xi;
+    P.r_dt = (float)(prm->r * prm->dt);
+    P.half_dt = (float)(0.5 * prm->dt);
+    P.sq_dt = (float)sqrt(prm->dt);
+    P.rho = (float)prm->rho;
+    P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);
+    P.n = n;
+    P.n_paths = ps->n_paths;
+    P.ld = ps->ld;
+    P.path_offset = path_offset;
+    P.ld_draws = mcp_round_up(ps->n_paths, 32);
+
+    // device tables (+ slot-major draw tables when injecting / dumping) live in the ctx scratch
+    const int Mp = P.Mp;
+    const size_t tab_bytes = (size_t)Mp * (8 + 8 + 4 + 4);
+    const bool use_draws = injected || dump;
+    const int64_t pc_max = use_draws ? (int64_t)((256u << 20) / ((size_t)4 * n * 4 * 2)) / 32 * 32 : 0;  // paths per draw chunk
+    if (use_draws && pc_max < 32) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: draw staging too small for n=%d", n);
+    const int64_t pc = use_draws ? (ps->n_paths < pc_max ? mcp_round_up(ps->n_paths, 32) : pc_max) : 0;
+    const size_t draws_bytes = use_draws ? (size_t)4 * n * (size_t)pc * 4 : 0;
+    MCP_TRY(mcp_scratch_reserve(ctx, mcp_round_up((int64_t)tab_bytes, 256) + 2 * draws_bytes));
+    unsigned char* base = (unsigned char*)ctx->scratch;
+    float2* d_phis = (float2*)base;
+    float2* d_tw = d_phis + Mp;
+    float* d_comp2 = (float*)(d_tw + Mp);
+    int* d_pos = (int*)(d_comp2 + Mp);
+    float* d_slot = (float*)(base + mcp_round_up((int64_t)tab_bytes, 256));  // [4n][pc]  slot-major
+    float* d_rows = d_slot + (size_t)4 * n * pc;                             // [pc][4n]  host order
+    MCP_CUDA(ctx, cudaMemcpyAsync(d_phis, phis.data(), (size_t)Mp * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaMemcpyAsync(d_tw, tw.data(), (size_t)Mp * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaMemcpyAsync(d_comp2, comp2.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaMemcpyAsync(d_pos, pos.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+
+    const PhiloxKeys K = philox_make_keys(seed);
+    int TP = 32;
+    while (TP > 4 && smem_bytes(Mp, TP) > 200 * 1024) TP >>= 1;
+    if (smem_bytes(Mp, TP) > 227 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n_steps %d needs too much shared memory", n);
+
+    auto run = [&](const RbParams& Q, const float* din, float* dout, float* out) -> int {
+        switch (TP) {
+            case 32: return launch_tp<32>(ctx, Q, K, d_phis, d_tw, d_comp2, d_pos, din, dout, out);
+            case 16: return launch_tp<16>(ctx, Q, K, d_phis, d_tw, d_comp2, d_pos, din, dout, out);
+            case 8: return launch_tp<8>(ctx, Q, K, d_phis, d_tw, d_comp2, d_pos, din, dout, out);
+            default: return launch_tp<4>(ctx, Q, K, d_phis, d_tw, d_comp2, d_pos, din, dout, out);
+        }
+    };
+
+    if (!use_draws) return run(P, nullptr, nullptr, (float*)ps->data);
+
+    // injected / dumped draws: stream the host [path][4n] table in chunks, transposing on the device
+    const int slots = 4 * n;
+    for (int64_t p0 = 0; p0 < ps->n_paths; p0 += pc) {
+        const int64_t np = (ps->n_paths - p0 < pc) ? ps->n_paths - p0 : pc;
+        RbParams Q = P;
+        Q.n_paths = np;
+        Q.path_offset = path_offset + (uint64_t)p0;
+        Q.ld_draws = pc;
+        if (injected) {
+            MCP_CUDA(ctx, cudaMemcpyAsync(d_rows, injected + (size_t)p0 * slots, (size_t)np * slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+            mcp_launch_transpose<float, float>(ctx->stream, d_rows, slots, np, slots, d_slot, pc);
+            MCP_LAUNCH_CHECK(ctx);
+        }
+        // when both are requested the dump simply echoes the injected values (same table, in place)
+        MCP_TRY(run(Q, injected ? d_slot : nullptr, dump ? d_slot : nullptr, (float*)ps->data + p0));
+        if (dump) {
+            mcp_launch_transpose<float, float>(ctx->stream, d_slot, pc, slots, np, d_rows, slots);
+            MCP_LAUNCH_CHECK(ctx);
+            MCP_CUDA(ctx, cudaMemcpyAsync(dump + (size_t)p0 * slots, d_rows, (size_t)np * slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MCP_OK;
+}

@@ -1,0 +1,616 @@
+// lsm.cu -- Longstaff-Schwartz backward induction (the reference's value-iteration variant) on the device.
+//
+// Replaces LSM::PredictOptionPrice (src/models/LSMPricer.cpp:19-102):
+//   V_{M-1} = payoff(S_{M-1})                                              :37-40
+//   for j = M-2 .. 0:                                                      :42
+//     j dt > maturity      -> V_j = e^{-r dt} V_{j+1}                      :43-49
+//     ITM = { payoff(S_j) > 1e-14 }                                        :51-58
+//     c_j = argmin || [1,S,..,S^p] c - e^{-r dt} V_{j+1} ||  over ITM      :61-76  (Eigen bdcSvd, min-norm)
+//     ITM: V_j = max(payoff, basis(S_j) . c_j)                             :78-86
+//     payoff < 1e-14: V_j = e^{-r dt} V_{j+1}                              :89-94
+//   price = mean_i V_0[i]                                                  :97-101
+//
+// B200 design.  The reference materialises Values[N][M] doubles and, per step, an index list, a design
+// matrix and a thin SVD -- all strided over a path-major vector<vector>.  Here only a carry vector V lives
+// next to the time-major slab, and each time step is ONE streaming kernel:
+//   sweep(j):  read S_j, S_{j-1}, V;  apply the step-j decision with the already solved c_j;  write V;  and in
+//              the same pass accumulate the normal-equation moments of step j-1 from the V_j just produced
+//              (fused continuation/exercise update + discounted carry + next regression's X^T X, X^T y).
+//   solve(j-1): one CTA sums the per-CTA fp64 partials in a fixed order (bitwise reproducible), all-reduces
+//              them across GPUs when a communicator is attached (the ONLY data-path collective: 3p+2 doubles),
+//              and solves the (p+1)x(p+1) system.
+// Regression numerics.  X^T X in raw monomials of S~100 is singular in fp64 (cond ~ 4e17 at config 1), so
+// moments are accumulated in the standardised variable x = (S - mu_j) / s_j (mu_j, s_j = mean / std of the
+// in-the-money prices of a fixed leading sample of paths).  Any basis of the same polynomial space yields the
+// same fitted values at the regression points, which is all the reference evaluates (LSMPricer.cpp:82-85); the
+// Hankel structure needs only sum x^k (k <= 2p) and sum x^k y (k <= p).  Rank-deficient steps (j = 0: all paths
+// at S0; fewer ITM paths than basis functions) reproduce the min-norm / projection behaviour through a Jacobi
+// eigen-decomposition with a relative cut, the normal-equation image of Eigen's singular-value threshold.
+// All decisions are taken in fp64 on the stored path values, exactly like the reference.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int LSM_NT = 256;
+constexpr int MAXP = 6;
+constexpr int COEF_LD = 8;       // coefficient row stride (p+1 <= 7)
+constexpr int MOM_LD = 24;       // moment row stride (3p+2 <= 20)
+constexpr int SAMPLE_MAX = 16384;
+
+enum StepKind { STEP_NORMAL = 0, STEP_DISCOUNT = 1 };
+
+struct LsmDev {  // pointers into ctx scratch
+    double* coef;     // [M][COEF_LD]
+    double* mu;       // [M]
+    double* inv_s;    // [M]
+    double* ssum;     // [M][4]   sample sums: cnt, sum S, sum S^2
+    double* partial;  // [max_blocks][MOM_LD]
+    double* moments;  // [MOM_LD]
+    double* fin;      // [4]      sum V0, sum V0^2, n
+    int* kind;        // [M]
+};
+
+struct SweepArgs {
+    const void* S;   // slab
+    int64_t ld, n;   // row stride, paths
+    void* V;         // carry
+    int32_t* tau;    // first exercise index (nullable)
+    LsmDev d;
+    double K, disc;
+    int is_call;
+    int j;           // step being decided
+    int terminal;    // j == M-1: V = payoff
+    int do_moments;  // accumulate moments of step j-1
+    int do_final;    // j == 0: accumulate sum V, sum V^2
+};
+
+__device__ __forceinline__ double payoff_fn(int is_call, double S, double K) {  // include/core/common.h:8-14
+    const double x = is_call ? S - K : K - S;
+    return x > 0.0 ? x : 0.0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NV], double* __restrict__ partial_row) {
+    __shared__ double red[LSM_NT / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < LSM_NT / 32; ++w) s += red[w][threadIdx.x];
+        partial_row[threadIdx.x] = s;
+    }
+}
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, double (&o)[4]) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void store_round(float* p, double (&io)[4]) {  // stores and returns the stored values
+        float4 v = make_float4((float)io[0], (float)io[1], (float)io[2], (float)io[3]);
+        *reinterpret_cast<float4*>(p) = v;
+        io[0] = v.x; io[1] = v.y; io[2] = v.z; io[3] = v.w;
+    }
+};
+template <>
+struct Vec4<double> {
+    static __device__ __forceinline__ void load(const double* p, double (&o)[4]) {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+    static __device__ __forceinline__ void store_round(double* p, double (&io)[4]) {
+        *reinterpret_cast<double2*>(p) = make_double2(io[0], io[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(io[2], io[3]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep(j): the one streaming pass per time step.  ST = slab storage, CT = carry storage, P = poly order.
+// Algorithmic traffic per path: S_j + S_{j-1} reads, V read + write.
+// ---------------------------------------------------------------------------------------------------------
+template <typename ST, typename CT, int P>
+__global__ void __launch_bounds__(LSM_NT) lsm_sweep_kernel(SweepArgs a) {
+    constexpr int NM = 3 * P + 2;  // s[0..2P], t[0..P]
+    constexpr int NV = NM > 2 ? NM : 2;
+    const ST* __restrict__ Sj = reinterpret_cast<const ST*>(a.S) + (int64_t)a.j * a.ld;
+    const ST* __restrict__ Sp = reinterpret_cast<const ST*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    CT* __restrict__ V = reinterpret_cast<CT*>(a.V);
+
+    const int kind = a.d.kind[a.j];
+    double c[P + 1];
+#pragma unroll
+    for (int k = 0; k <= P; ++k) c[k] = a.d.coef[(int64_t)a.j * COEF_LD + k];
+    const double mu = a.d.mu[a.j], inv_s = a.d.inv_s[a.j];
+    const double mu_p = a.d.mu[a.j > 0 ? a.j - 1 : 0], inv_s_p = a.d.inv_s[a.j > 0 ? a.j - 1 : 0];
+
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+
+    const int64_t stride = (int64_t)gridDim.x * LSM_NT * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * LSM_NT + threadIdx.x) * 4; i < a.n; i += stride) {
+        double s[4], sp[4], v[4];
+        Vec4<ST>::load(Sj + i, s);
+        if (a.do_moments) Vec4<ST>::load(Sp + i, sp);
+        if (!a.terminal) Vec4<CT>::load(V + i, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double pay = payoff_fn(a.is_call, s[e], a.K);
+            double vn;
+            if (a.terminal) {
+                vn = pay;  // LSMPricer.cpp:37-40
+            } else if (kind == STEP_DISCOUNT) {
+                vn = v[e] * a.disc;  // LSMPricer.cpp:43-49
+            } else if (pay > 1e-14) {  // LSMPricer.cpp:78-86
+                const double x = (s[e] - mu) * inv_s;
+                double cont = c[P];
+#pragma unroll
+                for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
+                const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate
+                vn = ex ? pay : cont;
+                if (ex && a.tau && i + e < a.n) a.tau[i + e] = a.j;
+            } else if (pay < 1e-14) {  // LSMPricer.cpp:89-94
+                vn = v[e] * a.disc;
+            } else {
+                vn = 0.0;  // payoff == 1e-14 exactly: Values[i][j] keeps its initial 0 (LSMPricer.cpp:35)
+            }
+            v[e] = vn;
+        }
+        Vec4<CT>::store_round(V + i, v);  // v[] now holds exactly what the next step will read
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (i + e < a.n) {
+                if (a.do_moments) {
+                    if (payoff_fn(a.is_call, sp[e], a.K) > 1e-14) {  // LSMPricer.cpp:51-58 for step j-1
+                        const double x = (sp[e] - mu_p) * inv_s_p, y = v[e] * a.disc;  // LSMPricer.cpp:69
+                        double xp = 1.0;
+#pragma unroll
+                        for (int k = 0; k <= 2 * P; ++k) {
+                            acc[k] += xp;
+                            if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
+                            xp *= x;
+                        }
+                    }
+                }
+                if (a.do_final) acc[0] += v[e];
+            }
+        }
+    }
+    if (a.do_moments || a.do_final) block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+}
+
+// Sum the per-CTA partial rows in a fixed order -> out[0..nv).
+__global__ void __launch_bounds__(256) lsm_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
+    __shared__ double red[256];
+    for (int k = 0; k < nv; ++k) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * MOM_LD + k];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[k] = red[0];
+        __syncthreads();
+    }
+}
+
+// Solve the normal equations of one step from the (globally reduced) moments -> coef row.
+//   G[a][b] = s[a+b], rhs[a] = t[a].  Diagonal equilibration, Cholesky when safely positive definite, else
+//   Jacobi eigen-decomposition with pseudo-inverse (projection onto the realised column space).
+__global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* __restrict__ coef_row) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = p + 1;
+    double G[MAXP + 1][MAXP + 1], rhs[MAXP + 1], d[MAXP + 1], z[MAXP + 1];
+    for (int k = 0; k < COEF_LD; ++k) coef_row[k] = 0.0;
+    if (!(mom[0] > 0.0)) return;  // no in-the-money path at this step (LSMPricer.cpp:60)
+    for (int a = 0; a < n; ++a) {
+        d[a] = mom[2 * a] > 0.0 ? 1.0 / sqrt(mom[2 * a]) : 0.0;
+    }
+    for (int a = 0; a < n; ++a) {
+        for (int b = 0; b < n; ++b) G[a][b] = mom[a + b] * d[a] * d[b];
+        rhs[a] = mom[2 * p + 1 + a] * d[a];
+    }
+    // --- Cholesky attempt ---
+    double L[MAXP + 1][MAXP + 1];
+    bool ok = true;
+    for (int k = 0; k < n && ok; ++k) {
+        double piv = G[k][k];
+        for (int m = 0; m < k; ++m) piv -= L[k][m] * L[k][m];
+        if (!(piv > 1e-10)) { ok = false; break; }
+        const double lkk = sqrt(piv);
+        L[k][k] = lkk;
+        for (int i = k + 1; i < n; ++i) {
+            double s = G[i][k];
+            for (int m = 0; m < k; ++m) s -= L[i][m] * L[k][m];
+            L[i][k] = s / lkk;
+        }
+    }
+    if (ok) {
+        for (int i = 0; i < n; ++i) {
+            double s = rhs[i];
+            for (int m = 0; m < i; ++m) s -= L[i][m] * z[m];
+            z[i] = s / L[i][i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = z[i];
+            for (int m = i + 1; m < n; ++m) s -= L[m][i] * z[m];
+            z[i] = s / L[i][i];
+        }
+    } else {
+        // --- cyclic Jacobi on the symmetric G; Q accumulates eigenvectors (columns) ---
+        double Q[MAXP + 1][MAXP + 1];
+        for (int a = 0; a < n; ++a)
+            for (int b = 0; b < n; ++b) Q[a][b] = a == b ? 1.0 : 0.0;
+        for (int sweep = 0; sweep < 40; ++sweep) {
+            double off = 0.0;
+            for (int a = 0; a < n; ++a)
+                for (int b = a + 1; b < n; ++b) off += G[a][b] * G[a][b];
+            if (off < 1e-60) break;
+            for (int pp = 0; pp < n - 1; ++pp)
+                for (int q = pp + 1; q < n; ++q) {
+                    const double apq = G[pp][q];
+                    if (apq == 0.0) continue;
+                    const double theta = (G[q][q] - G[pp][pp]) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                    for (int k = 0; k < n; ++k) {
+                        const double gkp = G[k][pp], gkq = G[k][q];
+                        G[k][pp] = cs * gkp - sn * gkq;
+                        G[k][q] = sn * gkp + cs * gkq;
+                    }
+                    for (int k = 0; k < n; ++k) {
+                        const double gpk = G[pp][k], gqk = G[q][k];
+                        G[pp][k] = cs * gpk - sn * gqk;
+                        G[q][k] = sn * gpk + cs * gqk;
+                    }
+                    for (int k = 0; k < n; ++k) {
+                        const double qkp = Q[k][pp], qkq = Q[k][q];
+                        Q[k][pp] = cs * qkp - sn * qkq;
+                        Q[k][q] = sn * qkp + cs * qkq;
+                    }
+                }
+        }
+        double lmax = 0.0;
+        for (int a = 0; a < n; ++a) lmax = fmax(lmax, G[a][a]);
+        const double thr = lmax * (double)n * 64.0 * 2.220446049250313e-16;
+        for (int a = 0; a < n; ++a) z[a] = 0.0;
+        for (int e = 0; e < n; ++e) {
+            if (G[e][e] > thr) {
+                double proj = 0.0;
+                for (int a = 0; a < n; ++a) proj += Q[a][e] * rhs[a];
+                proj /= G[e][e];
+                for (int a = 0; a < n; ++a) z[a] += Q[a][e] * proj;
+            }
+        }
+    }
+    for (int a = 0; a < n; ++a) coef_row[a] = z[a] * d[a];
+}
+
+// Sample statistics for the standardisation: CTA j sums cnt / S / S^2 over the in-the-money prices of the
+// first `ns` paths of row j.
+template <typename ST>
+__global__ void __launch_bounds__(256) lsm_scale_sums_kernel(const ST* __restrict__ S, int64_t ld, int ns, double K, int is_call,
+                                                            double* __restrict__ ssum) {
+    const int j = blockIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < ns; i += 256) {
+        const double s = (double)S[(int64_t)j * ld + i];
+        if (payoff_fn(is_call, s, K) > 1e-14) { acc[0] += 1.0; acc[1] += s; acc[2] = fma(s, s, acc[2]); }
+    }
+    __shared__ double red[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 3; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        ssum[(int64_t)j * 4 + threadIdx.x] = s;
+    }
+}
+
+__global__ void lsm_scale_finalize_kernel(const double* __restrict__ ssum, int M, double K, double* __restrict__ mu, double* __restrict__ inv_s) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const double cnt = ssum[j * 4], s1 = ssum[j * 4 + 1], s2 = ssum[j * 4 + 2];
+    double m = K, sd = fabs(K) > 0.0 ? fabs(K) : 1.0;
+    if (cnt >= 2.0) {
+        m = s1 / cnt;
+        const double var = (s2 - cnt * m * m) / (cnt - 1.0);
+        if (var > 1e-12 * m * m) sd = sqrt(var);
+        else sd = fabs(m) > 0.0 ? fabs(m) : 1.0;
+    }
+    mu[j] = m;
+    inv_s[j] = 1.0 / sd;
+}
+
+template <typename CT>
+__global__ void lsm_copy_v0_kernel(const CT* __restrict__ V, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)V[i];
+}
+
+// Second pass of the payoff averaging: sum (V0 - mean)^2 with the (global) mean already known -- the
+// two-pass form keeps the standard error exact even when every V0 is identical (j = 0 in the money).
+template <typename CT>
+__global__ void __launch_bounds__(LSM_NT) lsm_sqdev_kernel(const CT* __restrict__ V, int64_t n, const double* __restrict__ fin,
+                                                          double* __restrict__ partial) {
+    const double mean = fin[0] / fin[2];
+    double acc[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LSM_NT) {
+        const double dlt = (double)V[i] - mean;
+        acc[0] = fma(dlt, dlt, acc[0]);
+    }
+    block_reduce_to_partial<1>(acc, partial + (int64_t)blockIdx.x * MOM_LD);
+}
+
+__global__ void lsm_fill_tau_kernel(int32_t* __restrict__ tau, int64_t n, int32_t val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tau[i] = val;
+}
+
+typedef void (*SweepFn)(SweepArgs);
+
+template <typename ST, typename CT>
+SweepFn pick_sweep(int p) {
+    switch (p) {
+        case 0: return lsm_sweep_kernel<ST, CT, 0>;
+        case 1: return lsm_sweep_kernel<ST, CT, 1>;
+        case 2: return lsm_sweep_kernel<ST, CT, 2>;
+        case 3: return lsm_sweep_kernel<ST, CT, 3>;
+        case 4: return lsm_sweep_kernel<ST, CT, 4>;
+        case 5: return lsm_sweep_kernel<ST, CT, 5>;
+        default: return lsm_sweep_kernel<ST, CT, 6>;
+    }
+}
+
+SweepFn pick_sweep(int slab_dtype, int carry_dtype, int p) {
+    if (slab_dtype == MCP_F32) return carry_dtype == MCP_F32 ? pick_sweep<float, float>(p) : pick_sweep<float, double>(p);
+    return carry_dtype == MCP_F32 ? pick_sweep<double, float>(p) : pick_sweep<double, double>(p);
+}
+
+// Express  cont(S) = sum_k c_k ((S - mu) inv_s)^k  in the requested output basis.
+void convert_coeffs(const double* c, int p, double mu, double inv_s, double K, int basis, double* out) {
+    // monomials in S
+    double mono[MAXP + 1] = {0}, pw[MAXP + 1] = {0}, tmp[MAXP + 1];
+    pw[0] = 1.0;  // ((S - mu) inv_s)^0
+    const double a0 = -mu * inv_s, a1 = inv_s;
+    for (int k = 0; k <= p; ++k) {
+        for (int m = 0; m <= p; ++m) mono[m] += c[k] * pw[m];
+        for (int m = 0; m <= p; ++m) tmp[m] = a0 * pw[m] + (m > 0 ? a1 * pw[m - 1] : 0.0);
+        for (int m = 0; m <= p; ++m) pw[m] = tmp[m];
+    }
+    if (basis == MCP_BASIS_MONOMIAL) {
+        for (int m = 0; m <= p; ++m) out[m] = mono[m];
+        return;
+    }
+    // Laguerre in u = S/K:  sum_m mono_m K^m u^m = sum_k b_k L_k(u),  L_k(u) = sum_m C(k,m) (-1)^m / m! u^m
+    double um[MAXP + 1], Kp = 1.0;
+    for (int m = 0; m <= p; ++m) { um[m] = mono[m] * Kp; Kp *= K; }
+    for (int k = p; k >= 0; --k) {
+        // leading coefficient of L_k is (-1)^k / k!
+        double fact = 1.0;
+        for (int m = 2; m <= k; ++m) fact *= m;
+        const double lead = ((k & 1) ? -1.0 : 1.0) / fact;
+        const double b = um[k] / lead;
+        out[k] = b;
+        double binom = 1.0, mf = 1.0;  // C(k,m), m!
+        for (int m = 0; m <= k; ++m) {
+            if (m > 0) { binom = binom * (double)(k - m + 1) / (double)m; mf *= m; }
+            um[m] -= b * binom * ((m & 1) ? -1.0 : 1.0) / mf;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_params* prm, mcp_lsm_result* res, double* coeffs,
+                             int32_t* first_exercise, double* v0) {
+    if (!ctx || !prm || !res) return MCP_ERR_INVALID;
+    if (!ps || ps->n_paths <= 0) return mcp_fail(ctx, MCP_ERR_EMPTY_PATHS, "LSM::PredictOptionPrice: Empty pricePaths.");
+    if (ps->ctx != ctx) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: pathset belongs to another ctx");
+    const int p = prm->poly_order;
+    if (p < 0) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: poly_order %d < 0", p);
+    if (p > MAXP) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm: poly_order %d > %d", p, MAXP);
+    if (prm->carry != MCP_F32 && prm->carry != MCP_F64) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: bad carry dtype");
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const int M = ps->n_steps + 1;
+    const int64_t N = ps->n_paths;
+    const size_t csz = prm->carry == MCP_F32 ? 4 : 8;
+    const uint64_t launches0 = ctx->launches;
+
+    SweepFn sweep = pick_sweep(ps->dtype, prm->carry, p);
+    int occ = 0;
+    MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep, LSM_NT, 0));
+    if (occ < 1) occ = 1;
+    int64_t grid = (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4);
+    const int64_t cap = (int64_t)ctx->sm_count * occ;
+    if (grid > cap) grid = cap;
+
+    // ---- workspace ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_coef = take((size_t)M * COEF_LD * 8), o_mu = take((size_t)M * 8), o_is = take((size_t)M * 8);
+    const size_t o_ssum = take((size_t)M * 4 * 8), o_part = take((size_t)grid * MOM_LD * 8), o_mom = take(MOM_LD * 8);
+    const size_t o_fin = take(4 * 8), o_kind = take((size_t)M * 4);
+    MCP_TRY(mcp_scratch_reserve(ctx, off));
+    const size_t v_bytes = (size_t)mcp_round_up(N, 128) * csz;
+    const size_t tau_bytes = first_exercise ? (size_t)mcp_round_up(N, 128) * 4 : 0;
+    const size_t v0_bytes = v0 ? (size_t)mcp_round_up(N, 128) * 8 : 0;
+    MCP_TRY(mcp_carry_reserve(ctx, v_bytes + tau_bytes + v0_bytes));
+    unsigned char* sb = (unsigned char*)ctx->scratch;
+    LsmDev d;
+    d.coef = (double*)(sb + o_coef); d.mu = (double*)(sb + o_mu); d.inv_s = (double*)(sb + o_is); d.ssum = (double*)(sb + o_ssum);
+    d.partial = (double*)(sb + o_part); d.moments = (double*)(sb + o_mom); d.fin = (double*)(sb + o_fin); d.kind = (int*)(sb + o_kind);
+    void* dV = ctx->carry;
+    int32_t* dTau = first_exercise ? (int32_t*)((unsigned char*)ctx->carry + v_bytes) : nullptr;
+    double* dV0 = v0 ? (double*)((unsigned char*)ctx->carry + v_bytes + tau_bytes) : nullptr;
+
+    // step kinds: `thisTime = j * dt; if (thisTime > maturity)` evaluated in double exactly as LSMPricer.cpp:43-44
+    std::vector<int> kind(M, STEP_NORMAL);
+    for (int j = 0; j < M; ++j) kind[j] = ((double)j * prm->dt > prm->maturity) ? STEP_DISCOUNT : STEP_NORMAL;
+    const double disc = exp(-prm->r * prm->dt);  // LSMPricer.cpp:46,69,92
+
+    cudaStream_t st = ctx->stream;
+    MCP_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    MCP_CUDA(ctx, cudaMemcpyAsync(d.kind, kind.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    MCP_CUDA(ctx, cudaMemsetAsync(d.coef, 0, (size_t)M * COEF_LD * 8, st));
+
+    // ---- standardisation tables from a fixed leading sample of this rank's paths (summed over ranks) ----
+    const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
+    if (ps->dtype == MCP_F32) lsm_scale_sums_kernel<float><<<M, 256, 0, st>>>((const float*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
+    else lsm_scale_sums_kernel<double><<<M, 256, 0, st>>>((const double*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
+    MCP_LAUNCH_CHECK(ctx);
+    MCP_TRY(mcp_allreduce_f64(ctx, d.ssum, M * 4));
+    lsm_scale_finalize_kernel<<<(M + 127) / 128, 128, 0, st>>>(d.ssum, M, prm->strike, d.mu, d.inv_s);
+    MCP_LAUNCH_CHECK(ctx);
+    if (dTau) {
+        lsm_fill_tau_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dTau, N, (int32_t)(M - 1));
+        MCP_LAUNCH_CHECK(ctx);
+    }
+
+    // ---- backward sweep ----
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
+    a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
+    const int nm = 3 * p + 2;
+    for (int j = M - 1; j >= 0; --j) {
+        a.j = j;
+        a.terminal = (j == M - 1);
+        a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
+        a.do_final = (j == 0);
+        sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
+        MCP_LAUNCH_CHECK(ctx);
+        if (a.do_moments) {
+            lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, nm, d.moments);
+            MCP_LAUNCH_CHECK(ctx);
+            MCP_TRY(mcp_allreduce_f64(ctx, d.moments, nm));
+            lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD);
+            MCP_LAUNCH_CHECK(ctx);
+        }
+    }
+    // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
+    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, 1, d.fin);
+    MCP_LAUNCH_CHECK(ctx);
+    double fin[3] = {0, 0, 0};
+    const double nloc = (double)N;
+    MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below
+    if (prm->carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
+    else lsm_sqdev_kernel<double><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
+    MCP_LAUNCH_CHECK(ctx);
+    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, 1, d.fin + 1);
+    MCP_LAUNCH_CHECK(ctx);
+    MCP_TRY(mcp_allreduce_f64(ctx, d.fin + 1, 1));
+    MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    MCP_CUDA(ctx, cudaMemcpyAsync(fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (dV0) {
+        if (prm->carry == MCP_F32) lsm_copy_v0_kernel<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)dV, N, dV0);
+        else lsm_copy_v0_kernel<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const double*)dV, N, dV0);
+        MCP_LAUNCH_CHECK(ctx);
+        MCP_CUDA(ctx, cudaMemcpyAsync(v0, dV0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (dTau) MCP_CUDA(ctx, cudaMemcpyAsync(first_exercise, dTau, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<double> hcoef, hmu, his;
+    if (coeffs) {
+        hcoef.resize((size_t)M * COEF_LD); hmu.resize(M); his.resize(M);
+        MCP_CUDA(ctx, cudaMemcpyAsync(hcoef.data(), d.coef, (size_t)M * COEF_LD * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, cudaMemcpyAsync(hmu.data(), d.mu, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, cudaMemcpyAsync(his.data(), d.inv_s, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    }
+    MCP_CUDA(ctx, cudaStreamSynchronize(st));
+    MCP_CUDA(ctx, cudaGetLastError());
+
+    const double ng = fin[2];
+    res->sum_v0 = fin[0];
+    res->sum_sq_dev = fin[1];
+    res->n_paths_global = (int64_t)llround(ng);
+    res->price = fin[0] / ng;
+    const double var = ng > 1.0 ? fin[1] / (ng - 1.0) : 0.0;
+    res->std_error = var > 0.0 ? sqrt(var / ng) : 0.0;
+    float ms = 0.f;
+    MCP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->elapsed_ms = ms;
+    res->n_kernel_launches = (int)(ctx->launches - launches0);
+    if (coeffs) {
+        for (int j = 0; j + 1 < M; ++j) {
+            double* out = coeffs + (size_t)j * (p + 1);
+            bool any = false;
+            for (int k = 0; k <= p; ++k) any = any || hcoef[(size_t)j * COEF_LD + k] != 0.0;
+            if (!any) { for (int k = 0; k <= p; ++k) out[k] = 0.0; continue; }
+            convert_coeffs(&hcoef[(size_t)j * COEF_LD], p, hmu[j], his[j], prm->strike, prm->basis, out);
+        }
+    }
+    return MCP_OK;
+}
+
+extern "C" int mcp_lsm_price_host_rows(mcp_ctx* ctx, const double* const* rows, int64_t n_paths, int n_cols, double r, double strike,
+                                       double maturity, double dt, int is_call, int poly_order, double* price) {
+    if (!ctx || !price) return MCP_ERR_INVALID;
+    if (!rows || n_paths <= 0 || n_cols <= 0) return mcp_fail(ctx, MCP_ERR_EMPTY_PATHS, "LSM::PredictOptionPrice: Empty pricePaths.");
+    mcp_pathset* ps = nullptr;
+    MCP_TRY(mcp_pathset_create(ctx, n_paths, n_cols - 1, MCP_F64, &ps));
+    int rc = mcp_pathset_upload_rows_f64(ps, rows);
+    if (rc == MCP_OK) {
+        mcp_lsm_params prm;
+        prm.r = r; prm.strike = strike; prm.maturity = maturity; prm.dt = dt;
+        prm.is_call = is_call; prm.poly_order = poly_order; prm.basis = MCP_BASIS_MONOMIAL; prm.carry = MCP_F64;
+        mcp_lsm_result res;
+        rc = mcp_lsm_price(ctx, ps, &prm, &res, nullptr, nullptr, nullptr);
+        if (rc == MCP_OK) *price = res.price;
+    }
+    mcp_pathset_destroy(ps);
+    return rc;
+}
+
+extern "C" int mcp_price_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_params* model, const mcp_lsm_params* lsm, int64_t n_paths, int n_steps,
+                                      uint64_t seed, uint64_t path_offset, mcp_lsm_result* res, float* gen_ms) {
+    if (!ctx || !model || !lsm || !res) return MCP_ERR_INVALID;
+    mcp_pathset* ps = ctx->cached_ps;
+    if (!ps || ps->n_paths != n_paths || ps->n_steps != n_steps || ps->dtype != MCP_F32) {
+        if (ps) mcp_pathset_destroy(ps);
+        ctx->cached_ps = nullptr;
+        MCP_TRY(mcp_pathset_create(ctx, n_paths, n_steps, MCP_F32, &ps));
+        ctx->cached_ps = ps;
+    }
+    cudaEvent_t g0, g1;
+    MCP_CUDA(ctx, cudaEventCreate(&g0));
+    MCP_CUDA(ctx, cudaEventCreate(&g1));
+    MCP_CUDA(ctx, cudaEventRecord(g0, ctx->stream));
+    int rc = mcp_gen_rbergomi(ctx, ps, model, seed, path_offset, nullptr, nullptr);
+    if (rc == MCP_OK) {
+        cudaEventRecord(g1, ctx->stream);
+        rc = mcp_lsm_price(ctx, ps, lsm, res, nullptr, nullptr, nullptr);
+        if (rc == MCP_OK && gen_ms) cudaEventElapsedTime(gen_ms, g0, g1);
+    }
+    cudaEventDestroy(g0);
+    cudaEventDestroy(g1);
+    return rc;
+}

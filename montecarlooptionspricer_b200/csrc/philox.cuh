@@ -1,0 +1,62 @@
+// philox.cuh -- counter-based normal generation on the device: Philox4x32-10 + Box-Muller, no cuRAND.
+//
+// The reference draws from std::mt19937 re-seeded from std::random_device three times per path
+// (RoughVolatility.cpp:238-262): sequential, stateful and non-reproducible.  A counter-based generator has
+// no state to carry, so any (path, step) cell can be produced by any thread and results do not depend on
+// the launch geometry or the number of GPUs.  Stream layout (must match oracle/port/mcp_oracle.c):
+//   rough-vol: ctr = (g_lo, g_hi, k, 0)   -> (x0,x1) => (Zre_k, Zim_k),  (x2,x3) => (W1_k, W2_k)
+//   gbm      : ctr = (g_lo, g_hi, q, 1)   -> normals of steps 4q .. 4q+3
+// with g the GLOBAL path id and key = 64-bit seed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MCP_PHILOX_M0 0xD2511F53u
+#define MCP_PHILOX_M1 0xCD9E8D57u
+#define MCP_PHILOX_W0 0x9E3779B9u
+#define MCP_PHILOX_W1 0xBB67AE85u
+
+// The ten round keys depend only on the seed: computed once on the host and passed by value in the kernel
+// parameter block, so every LOP3 of the rounds takes its key straight from the constant bank.
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+static inline PhiloxKeys philox_make_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k0[r] = a;
+        K.k1[r] = b;
+        a += MCP_PHILOX_W0;
+        b += MCP_PHILOX_W1;
+    }
+    return K;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t lo0 = MCP_PHILOX_M0 * c0, hi0 = __umulhi(MCP_PHILOX_M0, c0);
+        const uint32_t lo1 = MCP_PHILOX_M1 * c2, hi1 = __umulhi(MCP_PHILOX_M1, c2);
+        c0 = hi1 ^ c1 ^ K.k0[r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ K.k1[r];
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Box-Muller in fp32: u1 = (a + 0.5) 2^-32 in (0,1], angle = 2 pi (b + 0.5) 2^-32.
+// lg2.approx / sin.approx / cos.approx on the SFU pipe: |error| ~ 1e-6 absolute on a normal, immaterial
+// next to Monte-Carlo noise and far inside the 1e-5 path tolerance (injected-draw parity never runs this).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float th = fmaf(__uint2float_rn(b), 1.4629180792671596e-09f, 7.314590396335798e-10f);  // 2pi * 2^-32 (b + 0.5)
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));                                  // -2 ln u1 = -2 ln2 log2 u1
+    float s, c;
+    __sincosf(th, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}

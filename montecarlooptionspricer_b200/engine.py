@@ -1,0 +1,238 @@
+"""Host-side handles over the C ABI: Engine (mcp_ctx) and PathSet (mcp_pathset).
+
+Thin by design -- argument marshalling only.  numpy arrays are HOST buffers handed to the C ABI, which does
+its own host<->device copies; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import GbmParams, LsmParams, LsmResult, McpError, RbergomiParams
+
+
+@dataclass
+class LsmOutput:
+    price: float
+    std_error: float
+    sum_v0: float
+    sum_sq_dev: float
+    n_paths_global: int
+    elapsed_ms: float
+    n_kernel_launches: int
+    coeffs: Optional[np.ndarray] = None
+    first_exercise: Optional[np.ndarray] = None
+    v0: Optional[np.ndarray] = None
+
+
+class Engine:
+    """One engine per host thread / per GPU rank (mcp_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._L = capi.lib()
+        h = C.c_void_p()
+        rc = self._L.mcp_create(device, C.byref(h))
+        if rc != 0:
+            raise McpError(rc, self._L.mcp_last_error(None).decode())
+        self._h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise McpError(rc, self._L.mcp_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mcp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._chk(self._L.mcp_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._chk(self._L.mcp_synchronize(self._h))
+
+    def device_info(self) -> dict:
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        fr, to = C.c_size_t(), C.c_size_t()
+        self._chk(self._L.mcp_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(fr), C.byref(to)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), free_bytes=fr.value, total_bytes=to.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.mcp_launch_count(self._h))
+
+    # -- multi-GPU --------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = capi.lib()
+        buf = C.create_string_buffer(128)
+        rc = L.mcp_comm_unique_id(buf)
+        if rc != 0:
+            raise McpError(rc, L.mcp_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._chk(self._L.mcp_comm_init(self._h, rank, nranks, buf))
+
+    def comm_info(self):
+        r, n = C.c_int(), C.c_int()
+        self._chk(self._L.mcp_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    # -- path sets --------------------------------------------------------------------------------
+    def pathset(self, n_paths: int, n_steps: int, dtype: int = capi.MCP_F32) -> "PathSet":
+        return PathSet(self, n_paths, n_steps, dtype)
+
+    def upload_paths(self, paths: np.ndarray, dtype: int = capi.MCP_F32) -> "PathSet":
+        """paths: host [n_paths][n_steps+1] (the reference's layout)."""
+        paths = np.ascontiguousarray(paths, dtype=np.float64)
+        if paths.ndim != 2 or paths.shape[0] == 0 or paths.shape[1] == 0:
+            raise McpError(capi.MCP_ERR_EMPTY_PATHS, "Empty pricePaths.")
+        ps = PathSet(self, paths.shape[0], paths.shape[1] - 1, dtype)
+        ps.upload(paths)
+        return ps
+
+    # -- generators -------------------------------------------------------------------------------
+    def gen_rbergomi(self, ps: "PathSet", S0, r, xi, H, eta, rho, dt, seed: int = 0, path_offset: int = 0,
+                     injected: Optional[np.ndarray] = None, dump: bool = False) -> Optional[np.ndarray]:
+        prm = RbergomiParams(S0, r, xi, H, eta, rho, dt)
+        n = ps.n_steps
+        inj = None
+        if injected is not None:
+            inj = np.ascontiguousarray(injected, dtype=np.float32)
+            assert inj.shape == (ps.n_paths, 4 * n), f"injected draws must be [{ps.n_paths}][{4 * n}]"
+        out = np.empty((ps.n_paths, 4 * n), dtype=np.float32) if dump else None
+        self._chk(self._L.mcp_gen_rbergomi(
+            self._h, ps._h, C.byref(prm), seed, path_offset,
+            inj.ctypes.data_as(capi._fp) if inj is not None else None,
+            out.ctypes.data_as(capi._fp) if out is not None else None))
+        return out
+
+    def gen_gbm(self, ps: "PathSet", S0, r, sigma, dt, seed: int = 0, path_offset: int = 0,
+                injected: Optional[np.ndarray] = None, dump: bool = False) -> Optional[np.ndarray]:
+        prm = GbmParams(S0, r, sigma, dt)
+        n = ps.n_steps
+        inj = None
+        if injected is not None:
+            inj = np.ascontiguousarray(injected, dtype=np.float32)
+            assert inj.shape == (ps.n_paths, n), f"injected draws must be [{ps.n_paths}][{n}]"
+        out = np.empty((ps.n_paths, n), dtype=np.float32) if dump else None
+        self._chk(self._L.mcp_gen_gbm(
+            self._h, ps._h, C.byref(prm), seed, path_offset,
+            inj.ctypes.data_as(capi._fp) if inj is not None else None,
+            out.ctypes.data_as(capi._fp) if out is not None else None))
+        return out
+
+    def philox_raw(self, seed: int, first: int, count: int, c2: int = 0, c3: int = 0) -> np.ndarray:
+        out = np.empty((count, 4), dtype=np.uint32)
+        self._chk(self._L.mcp_philox_raw(self._h, seed, first, count, c2, c3, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    # -- LSM --------------------------------------------------------------------------------------
+    def lsm_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, poly_order, basis: int = capi.MCP_BASIS_MONOMIAL,
+                  carry: int = capi.MCP_F64, want_coeffs: bool = False, want_first_exercise: bool = False,
+                  want_v0: bool = False) -> LsmOutput:
+        prm = LsmParams(r, strike, maturity, dt, int(bool(is_call)), poly_order, basis, carry)
+        res = LsmResult()
+        co = np.zeros((max(ps.n_steps, 1), poly_order + 1)) if want_coeffs else None
+        fe = np.zeros(ps.n_paths, dtype=np.int32) if want_first_exercise else None
+        v0 = np.zeros(ps.n_paths) if want_v0 else None
+        self._chk(self._L.mcp_lsm_price(
+            self._h, ps._h, C.byref(prm), C.byref(res),
+            co.ctypes.data_as(capi._dp) if co is not None else None,
+            fe.ctypes.data_as(capi._ip) if fe is not None else None,
+            v0.ctypes.data_as(capi._dp) if v0 is not None else None))
+        return LsmOutput(res.price, res.std_error, res.sum_v0, res.sum_sq_dev, res.n_paths_global, res.elapsed_ms,
+                         res.n_kernel_launches, co, fe, v0)
+
+    def lsm_price_host_rows(self, paths: np.ndarray, r, strike, maturity, dt, is_call, poly_order) -> float:
+        """The exact reference call shape: host [N][M] doubles in, the mean out (kept fp64 on the device)."""
+        paths = np.ascontiguousarray(paths, dtype=np.float64)
+        if paths.ndim != 2 or paths.size == 0:
+            rows, N, M = None, 0, 0
+        else:
+            N, M = paths.shape
+            rows = (capi._dp * N)(*[paths[i].ctypes.data_as(capi._dp) for i in range(N)])
+        px = C.c_double()
+        self._chk(self._L.mcp_lsm_price_host_rows(self._h, rows, N, M, r, strike, maturity, dt, int(bool(is_call)),
+                                                  poly_order, C.byref(px)))
+        return px.value
+
+    def price_rbergomi_lsm(self, model: dict, lsm: dict, n_paths: int, n_steps: int, seed: int = 0,
+                           path_offset: int = 0):
+        """Generate (native Philox) + LSM on the device: parameters in, a result out."""
+        m = RbergomiParams(model["S0"], model["r"], model["xi"], model["H"], model["eta"], model["rho"], model["dt"])
+        q = LsmParams(lsm["r"], lsm["strike"], lsm["maturity"], lsm["dt"], int(bool(lsm["is_call"])), lsm["poly_order"],
+                      lsm.get("basis", capi.MCP_BASIS_MONOMIAL), lsm.get("carry", capi.MCP_F32))
+        res = LsmResult()
+        gen_ms = C.c_float()
+        self._chk(self._L.mcp_price_rbergomi_lsm(self._h, C.byref(m), C.byref(q), n_paths, n_steps, seed, path_offset,
+                                                 C.byref(res), C.byref(gen_ms)))
+        out = LsmOutput(res.price, res.std_error, res.sum_v0, res.sum_sq_dev, res.n_paths_global, res.elapsed_ms,
+                        res.n_kernel_launches)
+        return out, gen_ms.value
+
+
+class PathSet:
+    """Device-resident time-major slab S[(n_steps+1)][ld] (mcp_pathset)."""
+
+    def __init__(self, eng: Engine, n_paths: int, n_steps: int, dtype: int = capi.MCP_F32):
+        self._eng = eng
+        self._L = eng._L
+        h = C.c_void_p()
+        eng._chk(self._L.mcp_pathset_create(eng._h, n_paths, n_steps, dtype, C.byref(h)))
+        self._h = h
+        self.n_paths, self.n_steps, self.dtype = n_paths, n_steps, dtype
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._eng, "_h", None):
+            self._L.mcp_pathset_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        n, s, ld, dt, p = C.c_int64(), C.c_int(), C.c_int64(), C.c_int(), C.c_void_p()
+        self._eng._chk(self._L.mcp_pathset_info(self._h, C.byref(n), C.byref(s), C.byref(ld), C.byref(dt), C.byref(p)))
+        return dict(n_paths=n.value, n_steps=s.value, ld=ld.value, dtype=dt.value, device_ptr=p.value)
+
+    def upload(self, paths: np.ndarray):
+        paths = np.ascontiguousarray(paths, dtype=np.float64)
+        assert paths.shape == (self.n_paths, self.n_steps + 1)
+        self._eng._chk(self._L.mcp_pathset_upload_f64(self._h, paths.ctypes.data_as(capi._dp), paths.shape[1]))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n_paths, self.n_steps + 1), dtype=np.float64)
+        self._eng._chk(self._L.mcp_pathset_download_f64(self._h, out.ctypes.data_as(capi._dp), out.shape[1]))
+        return out
+
+    def download_timemajor(self) -> np.ndarray:
+        out = np.empty((self.n_steps + 1, self.n_paths), dtype=np.float32)
+        self._eng._chk(self._L.mcp_pathset_download_timemajor_f32(self._h, out.ctypes.data_as(capi._fp), out.shape[1]))
+        return out

@@ -1,0 +1,187 @@
+"""GPU parity: Longstaff-Schwartz sweep vs the CPU oracle on IDENTICAL path values.
+
+Protocol: both sides price the same fp32-rounded path values (the GPU from its slab, the
+oracle from those values widened to double).  With the fp64 carry the exercise indices must be bit-exact
+(up to reported exact near-ties, expected 0) and the price agrees to ~1e-9; with the fp32 carry the price
+is within the stated 1e-5 relative tolerance."""
+import numpy as np
+import pytest
+
+import montecarlooptionspricer_b200 as m
+from conftest import CFG1, CFG2, f32_draws
+
+pytestmark = pytest.mark.gpu
+
+
+def gbm_paths(port, n_paths, n, seed, S0=100.0, r=0.05, sigma=0.2, T=1.0):
+    rng = np.random.default_rng(seed)
+    z = f32_draws(rng, (n_paths, n)).astype(np.float64)
+    p = port.gbm_paths(S0, r, sigma, T / n, n, z)
+    return p.astype(np.float32).astype(np.float64)  # the values both sides see
+
+
+def check_parity(engine, port, paths, r, K, T, dt, is_call, p, price_tol=1e-9):
+    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+    got = engine.lsm_price(ps, r, K, T, dt, is_call, p, carry=m.MCP_F64, want_coeffs=True, want_first_exercise=True, want_v0=True)
+    want = port.lsm(paths, r, K, T, dt, is_call, p)
+    ps.close()
+    assert abs(got.price - want["price"]) <= price_tol * max(1.0, abs(want["price"])), (got.price, want["price"])
+    assert abs(got.std_error - want["stderr"]) <= 1e-7 * want["stderr"] + 1e-12 * max(1.0, abs(want["price"]))
+    mism = np.nonzero(got.first_exercise != want["first_ex"])[0]
+    # a mismatch is only tolerated at an exact near-tie |payoff - cont| < 1e-9 K (none expected)
+    assert mism.size == 0 or want["min_gap"] < 1e-9 * K, f"{mism.size} exercise-index mismatches, min gap {want['min_gap']:.3e}"
+    assert mism.size <= 2
+    if mism.size == 0:
+        assert np.max(np.abs(got.v0 - want["V0"])) <= 1e-8 * max(1.0, np.max(np.abs(want["V0"])))
+    return got, want
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_lsm_config1_put_parity(engine, port, p):
+    """BASELINE config 1: American put under GBM, S0=K=100, r=.05, sigma=.2, T=1, 100k paths x 50 steps."""
+    paths = gbm_paths(port, 100_000, CFG1["n"], seed=1)
+    got, want = check_parity(engine, port, paths, CFG1["r"], CFG1["K"], CFG1["T"], CFG1["T"] / CFG1["n"], False, p)
+    if p == 3:  # value-iteration LSM is high-biased vs the Bermudan-50 value 6.0786
+        assert 6.0 < got.price < 6.2
+
+
+def test_lsm_high_order_is_outside_the_reference_parity_domain(engine, port):
+    """For polyOrder >= 5 the reference's RAW monomial design [1,S,..,S^p] with S~100 is numerically rank
+    deficient by Eigen's own rule (sigma_min < (p+1) eps sigma_max), so bdcSvd().solve() silently drops
+    directions (LSMPricer.cpp:76) and the result hinges on rounding of sub-threshold singular values.  The
+    device regresses in a standardised basis and keeps full rank; there the agreement is statistical."""
+    paths = gbm_paths(port, 100_000, 50, seed=1)
+    S = paths[:, 10]
+    sv = np.linalg.svd(np.vander(S[S < 100.0], 6, increasing=True), compute_uv=False)
+    assert sv[-1] < 6 * np.finfo(float).eps * sv[0]  # the reference truncates here
+    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+    got = engine.lsm_price(ps, 0.05, 100.0, 1.0, 0.02, False, 5)
+    want = port.lsm(paths, 0.05, 100.0, 1.0, 0.02, False, 5)
+    assert abs(got.price - want["price"]) < 3 * want["stderr"]
+    ps.close()
+
+
+def test_lsm_fitted_continuation_matches_oracle(engine, port):
+    """Coefficient tables are in different bases (device: standardised; oracle: raw monomials, min-norm) but the
+    fitted continuation FUNCTION must coincide on the in-the-money range wherever the design has full rank."""
+    paths = gbm_paths(port, 50_000, 50, seed=3)
+    got, want = check_parity(engine, port, paths, 0.05, 100.0, 1.0, 0.02, False, 3)
+    S = np.linspace(80, 99.5, 40)
+    for j in range(5, 49):
+        a = np.polyval(got.coeffs[j][::-1], S)
+        b = np.polyval(want["coeffs"][j][::-1], S)
+        assert np.max(np.abs(a - b)) < 1e-6 * np.max(np.abs(b)), j
+    lag = engine_lsm_coeffs(engine, paths, basis=m.MCP_BASIS_LAGUERRE)
+    from numpy.polynomial import laguerre
+    for j in (10, 30, 48):
+        a = laguerre.lagval(S / 100.0, lag[j])
+        b = np.polyval(want["coeffs"][j][::-1], S)
+        assert np.max(np.abs(a - b)) < 1e-6 * np.max(np.abs(b)), j
+
+
+def engine_lsm_coeffs(engine, paths, basis):
+    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+    out = engine.lsm_price(ps, 0.05, 100.0, 1.0, 0.02, False, 3, basis=basis, want_coeffs=True)
+    ps.close()
+    return out.coeffs
+
+
+def test_lsm_call_and_strikes(engine, port):
+    paths = gbm_paths(port, 20_000, 40, seed=4, sigma=0.35)
+    for is_call, K in [(True, 100.0), (True, 90.0), (False, 110.0), (False, 70.0), (True, 140.0)]:
+        check_parity(engine, port, paths, 0.03, K, 1.0, 1.0 / 40, is_call, 2)
+
+
+def test_lsm_rbergomi_paths_cubic(engine, port):
+    """Config-3 shape at oracle-friendly size: rough-vol paths, 252 steps, cubic basis."""
+    n_paths, n = 20_000, 252
+    ps = engine.pathset(n_paths, n)
+    engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], seed=3)
+    slab = ps.download_timemajor()
+    got = engine.lsm_price(ps, 0.05, 100.0, 1.0, CFG2["dt"], False, 3, carry=m.MCP_F64, want_first_exercise=True)
+    want = port.lsm_timemajor_f32(slab, 0.05, 100.0, 1.0, CFG2["dt"], False, 3)
+    assert abs(got.price - want["price"]) < 1e-9 * want["price"]
+    assert np.array_equal(got.first_exercise, want["first_ex"]) or want["min_gap"] < 1e-7
+    got32 = engine.lsm_price(ps, 0.05, 100.0, 1.0, CFG2["dt"], False, 3, carry=m.MCP_F32)
+    assert abs(got32.price - want["price"]) < 1e-5 * want["price"]
+    ps.close()
+
+
+def test_lsm_fp32_carry_within_stated_tolerance(engine, port):
+    paths = gbm_paths(port, 100_000, 50, seed=6)
+    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+    got = engine.lsm_price(ps, 0.05, 100.0, 1.0, 0.02, False, 3, carry=m.MCP_F32)
+    want = port.lsm(paths, 0.05, 100.0, 1.0, 0.02, False, 3)
+    assert abs(got.price - want["price"]) < 1e-5 * want["price"]  # north_star tolerance
+    ps.close()
+
+
+def test_lsm_maturity_cut(engine, port):
+    """More columns than maturity/dt: steps with j*dt > maturity only discount (LSMPricer.cpp:43-49)."""
+    paths = gbm_paths(port, 5_000, 60, seed=7)
+    for T in (0.5, 0.5 + 1e-12, 0.3333, 5.0, 0.0):
+        check_parity(engine, port, paths, 0.05, 100.0, T, 1.0 / 60, False, 2)
+
+
+def test_lsm_rank_deficient_and_edge_cases(engine, port):
+    rng = np.random.default_rng(8)
+    # j = 0 in the money: every path at the same S0 < K -> rank-1 design, min-norm fit = mean(y)
+    paths = gbm_paths(port, 4_000, 20, seed=9, S0=90.0)
+    check_parity(engine, port, paths, 0.05, 100.0, 1.0, 0.05, False, 3)
+    # fewer in-the-money paths than basis functions, and none at all
+    base = gbm_paths(port, 64, 10, seed=10, S0=100.0, sigma=0.05)
+    check_parity(engine, port, base, 0.05, 93.0, 1.0, 0.1, False, 3)
+    check_parity(engine, port, base, 0.05, 50.0, 1.0, 0.1, False, 3)
+    # tiny shapes: one path; one column; two columns
+    check_parity(engine, port, base[:1], 0.05, 101.0, 1.0, 0.1, False, 2)
+    check_parity(engine, port, base[:, :1], 0.05, 101.0, 1.0, 0.1, False, 2)
+    check_parity(engine, port, base[:7, :2], 0.05, 101.0, 1.0, 0.1, False, 2)
+    # duplicated prices (ties in S) and a ragged count that is not a multiple of the vector width
+    dup = np.repeat(gbm_paths(port, 333, 12, seed=11), 3, axis=0)[:997]
+    check_parity(engine, port, dup, 0.05, 100.0, 1.0, 1.0 / 12, False, 3)
+    _ = rng
+
+
+def test_lsm_fp64_slab_matches_reference_on_double_paths(engine, ref, port):
+    """The drop-in call shape: host double paths in (kept fp64 on the device), mean out."""
+    rng = np.random.default_rng(12)
+    z = rng.standard_normal((30_000, 50))
+    paths = port.gbm_paths(100.0, 0.05, 0.2, 0.02, 50, z)  # full double precision, NOT rounded
+    want = ref.lsm_price(paths, 0.05, 100.0, 1.0, 0.02, False, 2)
+    got = m.LSM(engine).PredictOptionPrice(paths, 0.05, 100.0, 1.0, 0.02, False, 2)
+    assert abs(got - want) < 1e-9 * want
+
+
+def test_lsm_reference_production_shape(engine, ref):
+    """The reference's real workload: 250 paths x floor(dte/365*252) steps, polyOrder 2 (PredictionGen.cpp:718-719,790)."""
+    rng = np.random.default_rng(13)
+    hist = 100 * np.exp(np.cumsum(0.012 * rng.standard_normal(400)))
+    for steps in (5, 21, 63, 126):
+        draws = rng.standard_normal(250 * 4 * steps)
+        paths, used = ref.generate_paths(hist, steps, 250, draws)
+        assert used == draws.size
+        K = hist[-1] * 1.02
+        want = ref.lsm_price(paths, 0.04, K, steps / 252.0, 1 / 252.0, False, 2)
+        got = m.LSM(engine).PredictOptionPrice(paths, 0.04, K, steps / 252.0, 1 / 252.0, False, 2)
+        assert abs(got - want) < 1e-8 * max(1.0, want), (steps, got, want)
+
+
+def test_lsm_empty_paths_error_contract(engine):
+    with pytest.raises(RuntimeError, match="Empty pricePaths"):
+        m.LSM(engine).PredictOptionPrice([], 0.05, 100.0, 1.0, 0.02, False, 2)
+    with pytest.raises(RuntimeError, match="Empty pricePaths"):
+        m.LSM(engine).PredictOptionPrice([[]], 0.05, 100.0, 1.0, 0.02, False, 2)
+
+
+def test_price_rbergomi_lsm_native_within_3se_of_oracle(engine, port):
+    """Native Philox end to end (config 3 shape) vs the oracle on an INDEPENDENT sample of the same size
+    (the value-iteration LSM has an in-sample fitting bias that depends on N, so sizes must match)."""
+    model = dict(S0=100.0, r=0.05, xi=0.04, H=0.1, eta=1.9, rho=-0.9, dt=1 / 252)
+    lsm = dict(r=0.05, strike=100.0, maturity=1.0, dt=1 / 252, is_call=False, poly_order=3, carry=m.MCP_F32)
+    out, gen_ms = engine.price_rbergomi_lsm(model, lsm, 1 << 15, 252, seed=2024)
+    d = port.rbergomi_draws(777, 0, 1 << 15, 252)
+    paths = port.rbergomi_paths(100.0, 0.05, 0.04, 0.1, 1.9, -0.9, 1 / 252, 252, d)
+    want = port.lsm(paths, 0.05, 100.0, 1.0, 1 / 252, False, 3)
+    se = np.hypot(out.std_error, want["stderr"])
+    assert abs(out.price - want["price"]) < 3 * se, (out.price, want["price"], se)
+    assert out.n_paths_global == 1 << 15 and gen_ms > 0
