@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workload on B200: rBergomi American-put LSM price, 64M paths x 252
+steps, cubic basis (BASELINE.json configs[2]), strong-scaled over N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU code on the host cores
+
+A "step" = one whole pricing pass: Philox normals -> rough-vol paths (time-major fp32 slab in HBM) -> LSM
+backward induction (fused per-step sweep, fp64 moments) -> price + standard error.  Prints ONE JSON line.
+
+  value      path-steps/s, device-resident loop (paths + carry + tables live in HBM; CUDA events)
+  e2e        same metric through the public host call mcp_price_rbergomi_lsm (host parameter structs in, host
+             result out; per-step table H2D + result D2H + all synchronisation inside the wall-clock region)
+  roofline   dominant kernel by time; `kernels` lists both hot kernels (generator: ALU/SFU-bound, reported
+             against its 4 B/path-step store; LSM sweep: HBM-bound, 12 B/path-step with the fp32 carry)
+  cpu_baseline  the reference's unmodified generator + LSM (oracle/_ref) on a bounded sample, all host threads
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PATHS_TOTAL = 1 << 26
+N_STEPS = 252
+MODEL = dict(S0=100.0, r=0.05, xi=0.04, H=0.1, eta=1.9, rho=-0.9, dt=1.0 / 252.0)
+STRIKE, MATURITY, POLY = 100.0, 1.0, 3
+METRIC, UNIT = "path-steps/sec", "path-steps/s"
+GEN_BYTES_PER_PATHSTEP = 4.0    # one fp32 store, time-major
+LSM_BYTES_PER_PATHSTEP = 12.0   # S read 4 + carry read 4 + carry write 4 (fp32 carry)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev: int):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_history(n=400, seed=20261018):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return 100.0 * np.exp(np.cumsum(0.0126 * rng.standard_normal(n)))  # ~20% annualised vol
+
+
+def run_reference_rows(paths_per_row: int, rows_per_thread: int, threads: int = 0):
+    """Reference CPU arm: its own GenerateStockPricePaths + LSM::PredictOptionPrice, parallel over rows exactly as
+    src/core/PredictionGen.cpp:542-546 does.  Returns (path-steps/s, dict)."""
+    from oracle import oracle as O
+    if O.have_ref():
+        ref = O.ref()
+        cores = ref.omp_max_threads() if threads <= 0 else threads
+        hist = synthetic_history()
+        n_rows = rows_per_thread * cores
+        out = ref.bench_rows(hist, n_rows, paths_per_row, N_STEPS, 0.05, float(hist[-1]), False, POLY, threads=cores)
+        ps = n_rows * paths_per_row * N_STEPS
+        return ps / out["seconds"], dict(kind="reference", cores=cores, seconds=out["seconds"], rows=n_rows,
+                                         paths_per_row=paths_per_row,
+                                         gen_share=out["gen_seconds_sum"] / max(1e-9, out["gen_seconds_sum"] + out["lsm_seconds_sum"]))
+    # port fallback (single thread): oracle restatement
+    import numpy as np
+    port = O.port()
+    t0 = time.perf_counter()
+    d = port.rbergomi_draws(1, 0, paths_per_row, N_STEPS)
+    paths = port.rbergomi_paths(MODEL["S0"], MODEL["r"], MODEL["xi"], MODEL["H"], MODEL["eta"], MODEL["rho"], MODEL["dt"], N_STEPS, d)
+    port.lsm(paths, 0.05, STRIKE, MATURITY, MODEL["dt"], False, POLY)
+    sec = time.perf_counter() - t0
+    return paths_per_row * N_STEPS / sec, dict(kind="port", cores=1, seconds=sec, rows=1, paths_per_row=paths_per_row, gen_share=None)
+
+
+def bench_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        v, info = run_reference_rows(paths_per_row=8192, rows_per_thread=6)
+        if i >= args.warmup:
+            vals.append((v, info["seconds"]))
+    value = sum(v for v, _ in vals) / len(vals)
+    sample = f"{info['rows']} independent rows x {info['paths_per_row']} paths x {N_STEPS} steps (generate + LSM p={POLY}) per step, omp over rows"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(s for _, s in vals) / len(vals), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "rBergomi American put LSM, 252 steps, cubic basis (BASELINE configs[2]) -- bounded CPU sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--paths-log2", type=int, default=26, help="total paths = 2^k (default 26 = BASELINE config 3)")
+    ap.add_argument("--carry", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        bench_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import montecarlooptionspricer_b200 as m
+
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_total = 1 << args.paths_log2
+    n_loc = n_total // world
+    path_offset = rank * n_loc
+    carry = m.MCP_F32 if args.carry == "f32" else m.MCP_F64
+    lsm_bytes = LSM_BYTES_PER_PATHSTEP if args.carry == "f32" else 20.0
+
+    stream = torch.cuda.current_stream()
+    eng = m.Engine(local_rank, stream=stream.cuda_stream)
+    if world > 1:
+        uid = [m.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0])
+
+    ps = eng.pathset(n_loc, N_STEPS)
+    model = dict(MODEL)
+    lsm = dict(r=MODEL["r"], strike=STRIKE, maturity=MATURITY, dt=MODEL["dt"], is_call=False, poly_order=POLY, carry=carry)
+
+    def step_device(seed):
+        eng.gen_rbergomi(ps, MODEL["S0"], MODEL["r"], MODEL["xi"], MODEL["H"], MODEL["eta"], MODEL["rho"], MODEL["dt"],
+                         seed=seed, path_offset=path_offset)
+        return eng.lsm_price(ps, MODEL["r"], STRIKE, MATURITY, MODEL["dt"], False, POLY, carry=carry)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for w in range(max(args.warmup, 0)):
+        out = step_device(1000 + w)
+    barrier()
+
+    # ---- timed region A: device-resident loop, CUDA events on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    lsm_ms_sum, price, se = 0.0, None, None
+    for k in range(args.steps):
+        out = step_device(1 + k)
+        lsm_ms_sum += out.elapsed_ms
+        price, se = out.price, out.std_error
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = n_total * N_STEPS / (ms_per_step * 1e-3)
+
+    # ---- timed region B: end to end through the public host call (host structs in, host result out) ----
+    ps.close()  # the host call owns (and caches) its own slab
+    for w in range(2):
+        eng.price_rbergomi_lsm(model, lsm, n_loc, N_STEPS, seed=2000 + w, path_offset=path_offset)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        out_e, gen_ms_e = eng.price_rbergomi_lsm(model, lsm, n_loc, N_STEPS, seed=1 + k, path_offset=path_offset)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = n_total * N_STEPS * args.steps / e2e_s
+    Mp = 256
+    h2d = Mp * (8 + 8 + 4 + 4) + (N_STEPS + 1) * 4 + 8     # phi/twiddle/compensator/position tables, step kinds, N
+    d2h = 3 * 8                                            # sum V0, sum sq dev, N
+
+    # ---- per-kernel durations (CUDA events around each launch of the two hot kernels; separate, untimed pass) ----
+    eng.set_profiling(True)
+    eng.price_rbergomi_lsm(model, lsm, n_loc, N_STEPS, seed=77, path_offset=path_offset)
+    prof = eng.profile()
+    eng.set_profiling(False)
+    peak, peak_src = peaks()
+    gen_gbs = GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1) / (prof["gen_kernel_ms"] * 1e-3) / 1e9
+    sweep_avg_ms = prof["sweep_kernels_ms"] / max(1, prof["n_sweep_launches"])
+    sweep_gbs = lsm_bytes * n_loc / (sweep_avg_ms * 1e-3) / 1e9
+    kernels = {
+        "rbergomi_paths_kernel": {"bound": "alu+sfu (reported vs its HBM store)", "launches_per_step": 1, "ms": prof["gen_kernel_ms"],
+                                  "algorithmic_bytes": GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1), "achieved_gbs": gen_gbs,
+                                  "frac_hbm": gen_gbs / peak},
+        "lsm_sweep_kernel": {"bound": "hbm", "launches_per_step": prof["n_sweep_launches"], "avg_ms": sweep_avg_ms,
+                             "total_ms": prof["sweep_kernels_ms"], "algorithmic_bytes_per_launch": lsm_bytes * n_loc,
+                             "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak,
+                             "lsm_total_ms_incl_solves_and_collectives": prof["lsm_total_ms"]},
+    }
+    dominant = "rbergomi_paths_kernel" if prof["gen_kernel_ms"] >= prof["sweep_kernels_ms"] else "lsm_sweep_kernel"
+    dk = kernels[dominant]
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dk["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "note": "generator is FP32/INT-ALU + SFU bound (see profiles/); the HBM-bound kernel is lsm_sweep_kernel",
+                "kernels": kernels}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own code on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = run_reference_rows(paths_per_row=8192, rows_per_thread=12)
+            cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                   "sample": f"{info['rows']} independent rows x {info['paths_per_row']} paths x {N_STEPS} steps, generate+LSM p={POLY}, "
+                             f"omp over rows as PredictionGen.cpp:542-546; {info['seconds']:.1f} s wall"}
+        except Exception as e:  # the checker must never take the bench down
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 paths / f64 regression moments / " + ("f32" if args.carry == "f32" else "f64") + " carry",
+            "data": "synthetic (native Philox4x32-10 normals, fixed seeds)",
+            "config": {"workload": f"rBergomi (H=0.1, eta=1.9, rho=-0.9) American put LSM, {n_total} paths x {N_STEPS} steps, cubic basis "
+                                   f"(BASELINE configs[2]); generate + price each step",
+                       "paths_total": n_total, "paths_per_gpu": n_loc, "n_steps": N_STEPS, "poly_order": POLY,
+                       "l2": "inputs exceed L2 (slab %.1f GB per GPU)" % (n_loc * (N_STEPS + 1) * 4 / 1e9),
+                       "parallelism": f"paths sharded x{world}; NCCL all-reduce of {3 * POLY + 2} fp64 moments per step"},
+            "time_to_price_s": ms_per_step * 1e-3, "lsm_price_time_s": lsm_ms_sum / args.steps * 1e-3,
+            "price": price, "std_error": se,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "mcp_price_rbergomi_lsm (host parameter structs in, host result struct out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

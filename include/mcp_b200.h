@@ -62,6 +62,17 @@ int mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, s
                     size_t *total_bytes);
 uint64_t mcp_launch_count(const mcp_ctx *ctx);  /* kernels launched by this ctx since creation */
 
+/* Optional per-kernel timing (CUDA events on the ctx stream around every launch of the two hot kernels).
+ * Off by default: the extra event records sit between launches and are not wanted in a throughput run. */
+typedef struct mcp_profile {
+    float gen_kernel_ms;    /* last mcp_gen_*: the path kernel alone */
+    float sweep_kernels_ms; /* last mcp_lsm_price: sum over its sweep launches */
+    int n_sweep_launches;
+    float lsm_total_ms;     /* last mcp_lsm_price: whole backward induction incl. solves / collectives */
+} mcp_profile;
+int mcp_set_profiling(mcp_ctx *ctx, int on);
+int mcp_get_profile(const mcp_ctx *ctx, mcp_profile *out);
+
 /* ---------------------------------------------------------------------------------------- multi-GPU
  * Paths shard across ranks (global path id = path_offset + local id); the only exchanged data are the
  * per-step regression moments and the final sums (NCCL all-reduce, fp64).  One ctx per rank/GPU. */

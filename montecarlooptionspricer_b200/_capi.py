@@ -33,6 +33,11 @@ class LsmResult(C.Structure):
                 ("n_paths_global", C.c_int64), ("elapsed_ms", C.c_float), ("n_kernel_launches", C.c_int)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("gen_kernel_ms", C.c_float), ("sweep_kernels_ms", C.c_float), ("n_sweep_launches", C.c_int),
+                ("lsm_total_ms", C.c_float)]
+
+
 _vp = C.c_void_p
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -49,6 +54,8 @@ SIGNATURES = {
     "mcp_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mcp_launch_count": (C.c_uint64, [_vp]),
+    "mcp_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "mcp_get_profile": (C.c_int, [_vp, C.POINTER(Profile)]),
     "mcp_comm_unique_id": (C.c_int, [_vp]),
     "mcp_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "mcp_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

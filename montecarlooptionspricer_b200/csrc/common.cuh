@@ -36,6 +36,10 @@ struct mcp_ctx {
     size_t carry_bytes = 0;
     // cached pathset for mcp_price_rbergomi_lsm
     mcp_pathset* cached_ps = nullptr;
+    // optional per-kernel timing
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // grow-only pool
+    mcp_profile prof = {0.f, 0.f, 0, 0.f};
 };
 
 struct mcp_pathset {
@@ -54,6 +58,8 @@ int mcp_pinned_reserve(mcp_ctx* ctx, size_t bytes);
 int mcp_carry_reserve(mcp_ctx* ctx, size_t bytes);
 // all-reduce (sum, fp64) of a device buffer on ctx->stream; no-op without a communicator
 int mcp_allreduce_f64(mcp_ctx* ctx, double* dev, int count);
+// event `i` of the profiling pool (created on demand)
+cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i);
 
 #define MCP_CUDA(ctx, call)                                                                            \
     do {                                                                                               \

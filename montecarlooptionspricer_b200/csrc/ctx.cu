@@ -108,6 +108,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->carry) cudaFree(ctx->carry);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -145,6 +146,18 @@ int mcp_device_info(mcp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, s
 
 uint64_t mcp_launch_count(const mcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mcp_set_profiling(mcp_ctx* ctx, int on) {
+    if (!ctx) return MCP_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return MCP_OK;
+}
+
+int mcp_get_profile(const mcp_ctx* ctx, mcp_profile* out) {
+    if (!ctx || !out) return MCP_ERR_INVALID;
+    *out = ctx->prof;
+    return MCP_OK;
+}
+
 int mcp_comm_unique_id(void* id128) {
     std::string why;
     if (!id128) return MCP_ERR_INVALID;
@@ -180,6 +193,15 @@ int mcp_comm_info(const mcp_ctx* ctx, int* rank, int* nranks) {
 }
 
 }  // extern "C"
+
+cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i) {
+    while (ctx->prof_ev.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        ctx->prof_ev.push_back(e);
+    }
+    return ctx->prof_ev[i];
+}
 
 int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MCP_OK;

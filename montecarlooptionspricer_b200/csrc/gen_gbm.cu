@@ -100,7 +100,16 @@ extern "C" int mcp_gen_gbm(mcp_ctx* ctx, mcp_pathset* ps, const mcp_gbm_params* 
         return MCP_OK;
     };
 
-    if (!injected && !dump) return launch(P, nullptr, nullptr, (float*)ps->data);
+    if (!injected && !dump) {
+        if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream);
+        MCP_TRY(launch(P, nullptr, nullptr, (float*)ps->data));
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            MCP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+            MCP_CUDA(ctx, cudaEventElapsedTime(&ctx->prof.gen_kernel_ms, ctx->ev0, ctx->ev1));
+        }
+        return MCP_OK;
+    }
 
     int64_t pc = (int64_t)((256u << 20) / ((size_t)n * 4 * 2)) / 32 * 32;
     if (pc < 32) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "gbm: draw staging too small for n=%d", n);

@@ -385,7 +385,16 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         }
     };
 
-    if (!use_draws) return run(P, nullptr, nullptr, (float*)ps->data);
+    if (!use_draws) {
+        if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream);
+        MCP_TRY(run(P, nullptr, nullptr, (float*)ps->data));
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            MCP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+            MCP_CUDA(ctx, cudaEventElapsedTime(&ctx->prof.gen_kernel_ms, ctx->ev0, ctx->ev1));
+        }
+        return MCP_OK;
+    }
 
     // injected / dumped draws: stream the host [path][4n] table in chunks, transposing on the device
     const int slots = 4 * n;

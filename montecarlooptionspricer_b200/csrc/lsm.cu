@@ -506,8 +506,10 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         a.terminal = (j == M - 1);
         a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
         a.do_final = (j == 0);
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j), st);
         sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
         MCP_LAUNCH_CHECK(ctx);
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j + 1), st);
         if (a.do_moments) {
             lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, nm, d.moments);
             MCP_LAUNCH_CHECK(ctx);
@@ -558,6 +560,17 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     float ms = 0.f;
     MCP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     res->elapsed_ms = ms;
+    ctx->prof.lsm_total_ms = ms;
+    ctx->prof.sweep_kernels_ms = 0.f;
+    ctx->prof.n_sweep_launches = 0;
+    if (ctx->profiling) {
+        for (int j = 0; j < M; ++j) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, mcp_prof_event(ctx, 2 * (size_t)j), mcp_prof_event(ctx, 2 * (size_t)j + 1)) == cudaSuccess)
+                ctx->prof.sweep_kernels_ms += t;
+            ctx->prof.n_sweep_launches++;
+        }
+    }
     res->n_kernel_launches = (int)(ctx->launches - launches0);
     if (coeffs) {
         for (int j = 0; j + 1 < M; ++j) {

@@ -81,6 +81,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._L.mcp_launch_count(self._h))
 
+    def set_profiling(self, on: bool):
+        self._chk(self._L.mcp_set_profiling(self._h, int(on)))
+
+    def profile(self) -> dict:
+        p = capi.Profile()
+        self._chk(self._L.mcp_get_profile(self._h, C.byref(p)))
+        return dict(gen_kernel_ms=p.gen_kernel_ms, sweep_kernels_ms=p.sweep_kernels_ms,
+                    n_sweep_launches=p.n_sweep_launches, lsm_total_ms=p.lsm_total_ms)
+
     # -- multi-GPU --------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
