@@ -99,18 +99,30 @@ __device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NV], doubl
     }
 }
 
+// Exact float -> double widening on the integer pipe (the F2F conversion unit is quarter rate and was the top
+// stall of the first sweep kernel: 44% of samples).  Sub-normals flush to zero (prices and option values never
+// are); zero, inf and nan keep their meaning.
+__device__ __forceinline__ double f2d(float f) {
+    const uint32_t b = __float_as_uint(f), e = b & 0x7f800000u;
+    uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+    uint32_t lo = b << 29;
+    if (e == 0u) { hi = b & 0x80000000u; lo = 0u; }
+    if (e == 0x7f800000u) hi |= 0x7ff00000u;
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 template <typename T>
 struct Vec4;
 template <>
 struct Vec4<float> {
     static __device__ __forceinline__ void load(const float* p, double (&o)[4]) {
         const float4 v = *reinterpret_cast<const float4*>(p);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        o[0] = f2d(v.x); o[1] = f2d(v.y); o[2] = f2d(v.z); o[3] = f2d(v.w);
     }
     static __device__ __forceinline__ void store_round(float* p, double (&io)[4]) {  // stores and returns the stored values
         float4 v = make_float4((float)io[0], (float)io[1], (float)io[2], (float)io[3]);
         *reinterpret_cast<float4*>(p) = v;
-        io[0] = v.x; io[1] = v.y; io[2] = v.z; io[3] = v.w;
+        io[0] = f2d(v.x); io[1] = f2d(v.y); io[2] = f2d(v.z); io[3] = f2d(v.w);
     }
 };
 template <>
@@ -125,19 +137,23 @@ struct Vec4<double> {
     }
 };
 
+// Vector index -> first path of the 4-wide vector.  Odd steps walk the slab backwards so that what the
+// previous launch touched last (still resident in the 126 MB L2: S_{j-1} and V) is what this launch reads first.
+__device__ __forceinline__ int64_t vec_base(int64_t idx, int64_t nvec, int j) { return ((j & 1) ? (nvec - 1 - idx) : idx) * 4; }
+
 // ---------------------------------------------------------------------------------------------------------
-// sweep(j): the one streaming pass per time step.  ST = slab storage, CT = carry storage, P = poly order.
-// Algorithmic traffic per path: S_j + S_{j-1} reads, V read + write.
+// sweep(j), PARITY kernel: every decision and every moment in fp64 on the stored values, exactly the
+// reference's arithmetic.  ST = slab storage, CT = carry storage, P = poly order.
 // ---------------------------------------------------------------------------------------------------------
 template <typename ST, typename CT, int P>
-__global__ void __launch_bounds__(LSM_NT) lsm_sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_kernel(SweepArgs a) {
     constexpr int NM = 3 * P + 2;  // s[0..2P], t[0..P]
     constexpr int NV = NM > 2 ? NM : 2;
     const ST* __restrict__ Sj = reinterpret_cast<const ST*>(a.S) + (int64_t)a.j * a.ld;
     const ST* __restrict__ Sp = reinterpret_cast<const ST*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
     CT* __restrict__ V = reinterpret_cast<CT*>(a.V);
 
-    const int kind = a.d.kind[a.j];
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];  // 0 regress/decide, 1 discount only, 2 terminal payoff
     double c[P + 1];
 #pragma unroll
     for (int k = 0; k <= P; ++k) c[k] = a.d.coef[(int64_t)a.j * COEF_LD + k];
@@ -147,56 +163,163 @@ __global__ void __launch_bounds__(LSM_NT) lsm_sweep_kernel(SweepArgs a) {
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    int cnt = 0;
 
-    const int64_t stride = (int64_t)gridDim.x * LSM_NT * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * LSM_NT + threadIdx.x) * 4; i < a.n; i += stride) {
+    const int64_t nvec = (a.n + 3) >> 2, vstride = (int64_t)gridDim.x * LSM_NT;
+    for (int64_t iv = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; iv < nvec; iv += vstride) {
+        const int64_t i = vec_base(iv, nvec, a.j);
+        const int nvalid = (int)(a.n - i < 4 ? a.n - i : 4);
         double s[4], sp[4], v[4];
         Vec4<ST>::load(Sj + i, s);
         if (a.do_moments) Vec4<ST>::load(Sp + i, sp);
-        if (!a.terminal) Vec4<CT>::load(V + i, v);
+        if (mode != 2) Vec4<CT>::load(V + i, v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const double pay = payoff_fn(a.is_call, s[e], a.K);
-            double vn;
-            if (a.terminal) {
-                vn = pay;  // LSMPricer.cpp:37-40
-            } else if (kind == STEP_DISCOUNT) {
-                vn = v[e] * a.disc;  // LSMPricer.cpp:43-49
-            } else if (pay > 1e-14) {  // LSMPricer.cpp:78-86
+            if (mode == 2) {
+                v[e] = pay;  // LSMPricer.cpp:37-40
+            } else if (mode == 1) {
+                v[e] = v[e] * a.disc;  // LSMPricer.cpp:43-49
+            } else {
                 const double x = (s[e] - mu) * inv_s;
                 double cont = c[P];
 #pragma unroll
                 for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
-                const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate
-                vn = ex ? pay : cont;
-                if (ex && a.tau && i + e < a.n) a.tau[i + e] = a.j;
-            } else if (pay < 1e-14) {  // LSMPricer.cpp:89-94
-                vn = v[e] * a.disc;
-            } else {
-                vn = 0.0;  // payoff == 1e-14 exactly: Values[i][j] keeps its initial 0 (LSMPricer.cpp:35)
+                const bool itm = pay > 1e-14;   // LSMPricer.cpp:55
+                const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate (LSMPricer.cpp:85)
+                const double carried = pay < 1e-14 ? v[e] * a.disc : 0.0;  // LSMPricer.cpp:89-94; == 1e-14 keeps the initial 0 (:35)
+                v[e] = itm ? (ex ? pay : cont) : carried;
+                if (a.tau && itm && ex && e < nvalid) a.tau[i + e] = a.j;
             }
-            v[e] = vn;
         }
         Vec4<CT>::store_round(V + i, v);  // v[] now holds exactly what the next step will read
+        if (a.do_moments) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (i + e < a.n) {
-                if (a.do_moments) {
-                    if (payoff_fn(a.is_call, sp[e], a.K) > 1e-14) {  // LSMPricer.cpp:51-58 for step j-1
-                        const double x = (sp[e] - mu_p) * inv_s_p, y = v[e] * a.disc;  // LSMPricer.cpp:69
-                        double xp = 1.0;
+            for (int e = 0; e < 4; ++e) {
+                if (e < nvalid && payoff_fn(a.is_call, sp[e], a.K) > 1e-14) {  // LSMPricer.cpp:51-58 for step j-1
+                    const double x = (sp[e] - mu_p) * inv_s_p, y = v[e] * a.disc;  // LSMPricer.cpp:69
+                    double xp = x;
+                    ++cnt;
+                    acc[2 * P + 1] += y;
 #pragma unroll
-                        for (int k = 0; k <= 2 * P; ++k) {
-                            acc[k] += xp;
-                            if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
-                            xp *= x;
-                        }
+                    for (int k = 1; k <= 2 * P; ++k) {
+                        acc[k] += xp;
+                        if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
+                        if (k < 2 * P) xp *= x;
                     }
                 }
-                if (a.do_final) acc[0] += v[e];
             }
         }
+        if (a.do_final) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < nvalid) acc[0] += v[e];
+        }
     }
+    if (a.do_moments) acc[0] = (double)cnt;
+    if (a.do_moments || a.do_final) block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep(j), THROUGHPUT kernel (fp32 slab + fp32 carry): all per-path arithmetic in fp32, only the cross-path
+// accumulation in fp64 (per-thread fp32 partial sums over <= 64 paths are folded into fp64 accumulators).
+// The kernel is then a pure HBM stream: 16 B/path of traffic (S_j, S_{j-1}, V in, V out), ~45 FP32 ops.
+// The discount is applied as a two-float product (d_hi + d_lo) so that 252 chained roundings stay unbiased;
+// the strike is split the same way.  Prices agree with the fp64 oracle to ~1e-7 relative (tolerance 1e-5);
+// exercise indices may differ from it at near-ties only (use the parity kernel when they must not).
+// ---------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast_kernel(SweepArgs a) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    constexpr int FLUSH = 8;  // iterations (x8 paths) between fp32 -> fp64 folds
+    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    float* __restrict__ V = reinterpret_cast<float*>(a.V);
+
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+    float c[P + 1];
+#pragma unroll
+    for (int k = 0; k <= P; ++k) c[k] = (float)a.d.coef[(int64_t)a.j * COEF_LD + k];
+    const float mu = (float)a.d.mu[a.j], inv_s = (float)a.d.inv_s[a.j];
+    const float mu_p = (float)a.d.mu[a.j > 0 ? a.j - 1 : 0], inv_s_p = (float)a.d.inv_s[a.j > 0 ? a.j - 1 : 0];
+    const float K_hi = (float)a.K, K_lo = (float)(a.K - (double)K_hi);
+    const float d_hi = (float)a.disc, d_lo = (float)(a.disc - (double)d_hi);
+    const float sgn = a.is_call ? 1.f : -1.f;
+
+    double acc[NV];
+    float la[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { acc[k] = 0.0; la[k] = 0.f; }
+    int since = 0;
+
+    const int64_t nvec = (a.n + 3) >> 2, npair = (nvec + 1) >> 1, pstride = (int64_t)gridDim.x * LSM_NT;
+    for (int64_t ip = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; ip < npair; ip += pstride) {
+        // two 4-wide vectors per iteration: 6 independent 16 B loads in flight per thread
+        const int64_t q = (a.j & 1) ? (npair - 1 - ip) : ip;
+        const int64_t i0 = q * 8, i1 = i0 + 4;
+        const bool has1 = i1 < a.n;
+        float4 s0 = *reinterpret_cast<const float4*>(Sj + i0), s1 = has1 ? *reinterpret_cast<const float4*>(Sj + i1) : s0;
+        float4 p0 = s0, p1 = s0, v0 = s0, v1 = s0;
+        if (a.do_moments) { p0 = *reinterpret_cast<const float4*>(Sp + i0); if (has1) p1 = *reinterpret_cast<const float4*>(Sp + i1); }
+        if (mode != 2) { v0 = *reinterpret_cast<const float4*>(V + i0); if (has1) v1 = *reinterpret_cast<const float4*>(V + i1); }
+        float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float sp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const int nvalid = (int)(a.n - i0 < 8 ? a.n - i0 : 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float pay = fmaxf(sgn * ((s[e] - K_hi) - K_lo), 0.f);  // include/core/common.h:8-14
+            if (mode == 2) {
+                v[e] = pay;
+            } else {
+                const float vd = fmaf(v[e], d_lo, v[e] * d_hi);
+                if (mode == 1) {
+                    v[e] = vd;
+                } else {
+                    const float x = (s[e] - mu) * inv_s;
+                    float cont = c[P];
+#pragma unroll
+                    for (int k = P - 1; k >= 0; --k) cont = fmaf(cont, x, c[k]);
+                    const bool itm = pay > 1e-14f, ex = !(pay < cont);
+                    v[e] = itm ? (ex ? pay : cont) : (pay < 1e-14f ? vd : 0.f);
+                    if (a.tau && itm && ex && e < nvalid) a.tau[i0 + e] = a.j;
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(V + i0) = make_float4(v[0], v[1], v[2], v[3]);
+        if (has1) *reinterpret_cast<float4*>(V + i1) = make_float4(v[4], v[5], v[6], v[7]);
+        if (a.do_moments) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float payp = fmaxf(sgn * ((sp[e] - K_hi) - K_lo), 0.f);
+                if (e < nvalid && payp > 1e-14f) {
+                    const float x = (sp[e] - mu_p) * inv_s_p, y = fmaf(v[e], d_lo, v[e] * d_hi);
+                    float xp = x;
+                    la[0] += 1.f;
+                    la[2 * P + 1] += y;
+#pragma unroll
+                    for (int k = 1; k <= 2 * P; ++k) {
+                        la[k] += xp;
+                        if (k <= P) la[2 * P + 1 + k] = fmaf(xp, y, la[2 * P + 1 + k]);
+                        if (k < 2 * P) xp *= x;
+                    }
+                }
+            }
+        }
+        if (a.do_final) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < nvalid) la[0] += v[e];
+        }
+        if (++since == FLUSH) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) { acc[k] += (double)la[k]; la[k] = 0.f; }
+            since = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] += (double)la[k];
     if (a.do_moments || a.do_final) block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
 }
 
@@ -389,8 +512,20 @@ SweepFn pick_sweep(int p) {
     }
 }
 
+SweepFn pick_sweep_fast(int p) {
+    switch (p) {
+        case 0: return lsm_sweep_fast_kernel<0>;
+        case 1: return lsm_sweep_fast_kernel<1>;
+        case 2: return lsm_sweep_fast_kernel<2>;
+        case 3: return lsm_sweep_fast_kernel<3>;
+        case 4: return lsm_sweep_fast_kernel<4>;
+        case 5: return lsm_sweep_fast_kernel<5>;
+        default: return lsm_sweep_fast_kernel<6>;
+    }
+}
+
 SweepFn pick_sweep(int slab_dtype, int carry_dtype, int p) {
-    if (slab_dtype == MCP_F32) return carry_dtype == MCP_F32 ? pick_sweep<float, float>(p) : pick_sweep<float, double>(p);
+    if (slab_dtype == MCP_F32) return carry_dtype == MCP_F32 ? pick_sweep_fast(p) : pick_sweep<float, double>(p);
     return carry_dtype == MCP_F32 ? pick_sweep<double, float>(p) : pick_sweep<double, double>(p);
 }
 
