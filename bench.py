@@ -118,7 +118,7 @@ def run_reference_rows(paths_per_row: int, rows_per_thread: int, threads: int = 
     import numpy as np
     port = O.port()
     t0 = time.perf_counter()
-    d = port.rbergomi_draws(1, 0, paths_per_row, N_STEPS)
+    d = port.rbergomi_draws(1, 0, paths_per_row, N_STEPS, MODEL["rho"])
     paths = port.rbergomi_paths(MODEL["S0"], MODEL["r"], MODEL["xi"], MODEL["H"], MODEL["eta"], MODEL["rho"], MODEL["dt"], N_STEPS, d)
     port.lsm(paths, 0.05, STRIKE, MATURITY, MODEL["dt"], False, POLY)
     sec = time.perf_counter() - t0

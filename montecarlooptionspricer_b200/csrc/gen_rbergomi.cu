@@ -33,14 +33,15 @@
 
 namespace {
 
-constexpr int NT = 256;  // threads per CTA
+constexpr int NT = 512;  // threads per CTA: 16 warps share one 32-path tile; 2 CTAs/SM -> 32 resident warps
 
 struct RbParams {
     float S0, xi, r_dt, half_dt, sq_dt, rho, rho_c;  // r*dt, 0.5*dt, sqrt(dt), rho, sqrt(1-rho^2)
     int n;        // steps
     int Mp;       // DFT length = nextPow2(n)
+    int lgMp;     // log2(Mp)
     int n_stage;  // DIF stages
-    int radix[4];
+    int lg_radix; // 2 bits per stage: log2(radix) of stage s at bits [2s, 2s+2)
     int64_t n_paths, ld;
     uint64_t path_offset;
     int64_t ld_draws;  // row stride of the slot-major draw tables
@@ -85,44 +86,85 @@ __device__ __forceinline__ void dft8(float2 (&x)[8]) {
     x[1] = b0; x[3] = b1; x[5] = b2; x[7] = b3;
 }
 
-// One DIF pass of radix R over sub-transforms of length L, for the TP paths of the tile.
-//   inputs  x_q = A[base + q*L/R],  outputs  y_s * w_L^{j s}  back to A[base + s*L/R]
-template <int R, int TP>
-__device__ __forceinline__ void dif_pass(float2* __restrict__ A, const float2* __restrict__ tw, int Mp, int L, int g, int p) {
-    constexpr int G = NT / TP;
-    const int stride = L / R;
-    const int tw_step = Mp / L;
-    for (int bf = g; bf < Mp / R; bf += G) {
-        const int blk = bf / stride, j = bf - blk * stride;
-        float2* a = A + (size_t)(blk * L + j) * TP + p;
-        float2 x[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[q] = a[(size_t)q * stride * TP];
-        if constexpr (R == 8) {
-            dft8(x);
-        } else if constexpr (R == 4) {
-            dft4(x[0], x[1], x[2], x[3]);
-        } else {
-            const float2 u = x[0];
-            x[0] = cadd(u, x[1]);
-            x[1] = csub(u, x[1]);
-        }
-        if (stride > 1) {
-#pragma unroll
-            for (int s = 1; s < R; ++s) x[s] = cmul(x[s], tw[(j * s * tw_step) & (Mp - 1)]);
-        }
-#pragma unroll
-        for (int s = 0; s < R; ++s) a[(size_t)s * stride * TP] = x[s];
+template <int R>
+__device__ __forceinline__ void dftR(float2 (&x)[R]) {
+    if constexpr (R == 8) {
+        dft8(x);
+    } else if constexpr (R == 4) {
+        dft4(x[0], x[1], x[2], x[3]);
+    } else {
+        const float2 u = x[0];
+        x[0] = cadd(u, x[1]);
+        x[1] = csub(u, x[1]);
     }
 }
 
+// One DIF pass of radix R = 2^LGR over sub-transforms of length L = 2^lgL, for the TP paths of the tile.
+//   inputs  x_q = A[base + q*L/R],  outputs  y_s * w_L^{j s}  back to A[base + s*L/R].  All index math is shifts.
+template <int LGR, int TP>
+__device__ __forceinline__ void dif_pass(float2* __restrict__ A, const float2* __restrict__ tw, int lgMp, int lgL, int g, int p) {
+    constexpr int R = 1 << LGR, G = NT / TP;
+    const int lgS = lgL - LGR, stride = 1 << lgS, Mp = 1 << lgMp;
+    for (int bf = g; bf < (Mp >> LGR); bf += G) {
+        const int blk = bf >> lgS, j = bf & (stride - 1);
+        float2* a = A + (size_t)((blk << lgL) + j) * TP + p;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = a[(size_t)(q << lgS) * TP];
+        dftR<R>(x);
+        if (lgS > 0) {
+            const int jt = j << (lgMp - lgL);
+#pragma unroll
+            for (int s = 1; s < R; ++s) x[s] = cmul(x[s], tw[(jt * s) & (Mp - 1)]);
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) a[(size_t)(s << lgS) * TP] = x[s];
+    }
+}
+
+// LAST pass (sub-transform length == radix, no twiddles).  Only Re(X) is ever used (RoughVolatility.cpp:277-281),
+// and this is the one place where every output X_m is in registers, so the variance and the log-increment
+//   v_m = xi exp(X_m - eta^2 t_m^{2H}/2),  d_m = (r - v_m/2) dt + sqrt(max(0,v_m)) sqrt(dt) dW_m      (:294-309, :356-363)
+// are formed right here and written over dW_m.  rev[] maps a storage position to its output index m.
+template <int LGR, int TP>
+__device__ __forceinline__ void last_pass(const float2* __restrict__ A, float* __restrict__ W, const int* __restrict__ rev,
+                                          const float* __restrict__ comp2, const RbParams& P, int g, int p) {
+    constexpr int R = 1 << LGR, G = NT / TP;
+    for (int bf = g; bf < (P.Mp >> LGR); bf += G) {
+        const float2* a = A + (size_t)(bf << LGR) * TP + p;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = a[(size_t)q * TP];
+        dftR<R>(x);
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const int m = rev[(bf << LGR) + s];
+            if (m < P.n) {
+                const float v = P.xi * fast_ex2(x[s].x + comp2[m]);
+                float* w = W + (size_t)m * TP + p;
+                *w = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * *w;
+            }
+        }
+    }
+}
+
+// Normals of one (path, step) in the native stream -- generic (slow) form, used for ragged chunks only.
+__device__ __forceinline__ void native_normals(uint32_t c0, uint32_t c1, int k, const PhiloxKeys& K, float& zr, float& zi, float& w) {
+    const uint4 xz = philox4x32_10(c0, c1, (uint32_t)(k >> 1), 0u, K);
+    if (k & 1) box_muller(xz.z, xz.w, zr, zi); else box_muller(xz.x, xz.y, zr, zi);
+    const uint4 xw = philox4x32_10(c0, c1, (uint32_t)(k >> 2), 2u, K);
+    float a, b;
+    if (k & 2) box_muller(xw.z, xw.w, a, b); else box_muller(xw.x, xw.y, a, b);
+    w = (k & 1) ? b : a;
+}
+
 // Dynamic shared memory carve-up (per CTA):
-//   float2 A[Mp][TP] | float W[Mp][TP] | float tot[G][TP] | float2 phis[Mp] | float2 tw[Mp] | float comp2[Mp] | int pos[Mp]
+//   float2 A[Mp][TP] | float W[Mp][TP] | float tot[G][TP] | float2 phis[Mp] | float2 tw[Mp] | float comp2[Mp] | int rev[Mp]
 template <int TP, bool INJECT, bool DUMP>
-__global__ void __launch_bounds__(NT) rbergomi_paths_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
-                                                           const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
-                                                           const int* __restrict__ g_pos, const float* __restrict__ draws_in,
-                                                           float* __restrict__ draws_out, float* __restrict__ out) {
+__global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
+                                                              const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
+                                                              const int* __restrict__ g_rev, const float* __restrict__ draws_in,
+                                                              float* __restrict__ draws_out, float* __restrict__ out) {
     constexpr int G = NT / TP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = P.Mp, n = P.n;
@@ -132,17 +174,18 @@ __global__ void __launch_bounds__(NT) rbergomi_paths_kernel(RbParams P, PhiloxKe
     float2* phis = reinterpret_cast<float2*>(tot + G * TP);
     float2* tw = phis + Mp;
     float* comp2 = reinterpret_cast<float*>(tw + Mp);
-    int* pos = reinterpret_cast<int*>(comp2 + Mp);
+    int* rev = reinterpret_cast<int*>(comp2 + Mp);
 
     const int tid = threadIdx.x, p = tid % TP, g = tid / TP;
     for (int i = tid; i < Mp; i += NT) {
         phis[i] = i < n ? g_phis[i] : make_float2(0.f, 0.f);
         tw[i] = g_tw[i];
         comp2[i] = i < n ? g_comp2[i] : 0.f;
-        pos[i] = g_pos[i];
+        rev[i] = g_rev[i];
     }
     const int CH = Mp >= G ? Mp / G : 1;  // contiguous time chunk owned by this thread
     const int k0 = g * CH, k1 = min(k0 + CH, Mp);
+    const bool has_chunk = k0 < Mp;
     const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
     __syncthreads();
 
@@ -152,62 +195,97 @@ __global__ void __launch_bounds__(NT) rbergomi_paths_kernel(RbParams P, PhiloxKe
         const uint64_t gid = P.path_offset + (uint64_t)path;
         const uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32);
 
-        // ---- phase 1: normals -> A = phis (.) Z (zero padded), W = rho W1 + rho_c W2 ------------------
-        if (g * CH < Mp) {
-#pragma unroll 2
-            for (int k = k0; k < k1; ++k) {
-                float2 a = make_float2(0.f, 0.f);
-                float w = 0.f;
-                if (k < n) {
-                    float zr, zi, w1, w2;
-                    if (INJECT) {
-                        const int64_t col = live ? path : 0;
-                        zr = draws_in[(int64_t)(2 * k) * P.ld_draws + col];
-                        zi = draws_in[(int64_t)(2 * k + 1) * P.ld_draws + col];
-                        w1 = draws_in[(int64_t)(2 * n + k) * P.ld_draws + col];
-                        w2 = draws_in[(int64_t)(3 * n + k) * P.ld_draws + col];
-                    } else {
-                        const uint4 x = philox4x32_10(c0, c1, (uint32_t)k, 0u, K);
-                        box_muller(x.x, x.y, zr, zi);
-                        box_muller(x.z, x.w, w1, w2);
+        // ---- phase 1: normals -> A = phis (.) Z (zero padded), W = dW mix --------------------------------
+        if (has_chunk) {
+            if (!INJECT && (CH & 3) == 0) {
+                // native stream, 4 steps at a time: 2 Philox calls -> 4 complex Z, 1 call -> 4 W
+                for (int kq = k0; kq < k1; kq += 4) {
+                    const uint4 xa = philox4x32_10(c0, c1, (uint32_t)(kq >> 1), 0u, K);
+                    const uint4 xb = philox4x32_10(c0, c1, (uint32_t)(kq >> 1) + 1u, 0u, K);
+                    const uint4 xw = philox4x32_10(c0, c1, (uint32_t)(kq >> 2), 2u, K);
+                    float z[8], w[4];
+                    box_muller(xa.x, xa.y, z[0], z[1]);
+                    box_muller(xa.z, xa.w, z[2], z[3]);
+                    box_muller(xb.x, xb.y, z[4], z[5]);
+                    box_muller(xb.z, xb.w, z[6], z[7]);
+                    box_muller(xw.x, xw.y, w[0], w[1]);
+                    box_muller(xw.z, xw.w, w[2], w[3]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int k = kq + t;
+                        const bool in = k < n;
+                        if (DUMP && live && in) {
+                            draws_out[(int64_t)(2 * k) * P.ld_draws + path] = z[2 * t];
+                            draws_out[(int64_t)(2 * k + 1) * P.ld_draws + path] = z[2 * t + 1];
+                            draws_out[(int64_t)(2 * n + k) * P.ld_draws + path] = P.rho * w[t];
+                            draws_out[(int64_t)(3 * n + k) * P.ld_draws + path] = P.rho_c * w[t];
+                        }
+                        A[(size_t)k * TP + p] = in ? cmul(phis[k], make_float2(z[2 * t], z[2 * t + 1])) : make_float2(0.f, 0.f);
+                        W[(size_t)k * TP + p] = in ? w[t] : 0.f;
                     }
-                    if (DUMP && live) {
-                        draws_out[(int64_t)(2 * k) * P.ld_draws + path] = zr;
-                        draws_out[(int64_t)(2 * k + 1) * P.ld_draws + path] = zi;
-                        draws_out[(int64_t)(2 * n + k) * P.ld_draws + path] = w1;
-                        draws_out[(int64_t)(3 * n + k) * P.ld_draws + path] = w2;
-                    }
-                    a = cmul(phis[k], make_float2(zr, zi));
-                    w = P.rho * w1 + P.rho_c * w2;
                 }
-                A[(size_t)k * TP + p] = a;
-                W[(size_t)k * TP + p] = w;
+            } else {
+                for (int k = k0; k < k1; ++k) {
+                    float2 a = make_float2(0.f, 0.f);
+                    float w = 0.f;
+                    if (k < n) {
+                        float zr, zi;
+                        if (INJECT) {
+                            const int64_t col = live ? path : 0;
+                            zr = draws_in[(int64_t)(2 * k) * P.ld_draws + col];
+                            zi = draws_in[(int64_t)(2 * k + 1) * P.ld_draws + col];
+                            w = P.rho * draws_in[(int64_t)(2 * n + k) * P.ld_draws + col] +
+                                P.rho_c * draws_in[(int64_t)(3 * n + k) * P.ld_draws + col];  // RoughVolatility.cpp:356-358
+                        } else {
+                            native_normals(c0, c1, k, K, zr, zi, w);
+                            if (DUMP && live) {
+                                draws_out[(int64_t)(2 * k) * P.ld_draws + path] = zr;
+                                draws_out[(int64_t)(2 * k + 1) * P.ld_draws + path] = zi;
+                                draws_out[(int64_t)(2 * n + k) * P.ld_draws + path] = P.rho * w;
+                                draws_out[(int64_t)(3 * n + k) * P.ld_draws + path] = P.rho_c * w;
+                            }
+                        }
+                        a = cmul(phis[k], make_float2(zr, zi));
+                    }
+                    A[(size_t)k * TP + p] = a;
+                    W[(size_t)k * TP + p] = w;
+                }
             }
         }
         __syncthreads();
 
-        // ---- phase 2: M'-point forward DFT in shared memory (digit-reversed output) -------------------
+        // ---- phase 2: M'-point forward DFT in shared memory; the last pass also forms the log-increments ----
         {
-            int L = Mp;
+            int lgL = P.lgMp;
             for (int s = 0; s < P.n_stage; ++s) {
-                const int R = P.radix[s];
-                if (R == 8) dif_pass<8, TP>(A, tw, Mp, L, g, p);
-                else if (R == 4) dif_pass<4, TP>(A, tw, Mp, L, g, p);
-                else dif_pass<2, TP>(A, tw, Mp, L, g, p);
-                L /= R;
+                const int lgR = (P.lg_radix >> (2 * s)) & 3;
+                if (s + 1 < P.n_stage) {
+                    if (lgR == 3) dif_pass<3, TP>(A, tw, P.lgMp, lgL, g, p);
+                    else if (lgR == 2) dif_pass<2, TP>(A, tw, P.lgMp, lgL, g, p);
+                    else dif_pass<1, TP>(A, tw, P.lgMp, lgL, g, p);
+                } else {
+                    if (lgR == 3) last_pass<3, TP>(A, W, rev, comp2, P, g, p);
+                    else if (lgR == 2) last_pass<2, TP>(A, W, rev, comp2, P, g, p);
+                    else last_pass<1, TP>(A, W, rev, comp2, P, g, p);
+                }
+                lgL -= lgR;
+                __syncthreads();
+            }
+            if (P.n_stage == 0) {  // n == 1: the transform is the identity
+                if (tid < TP) {
+                    const float v = P.xi * fast_ex2(A[p].x + comp2[0]);
+                    W[p] = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * W[p];
+                }
                 __syncthreads();
             }
         }
 
-        // ---- phase 3: variance, log-increments, chunk-local prefix sum --------------------------------
+        // ---- phase 3: log-space prefix sum over time: chunk-local scan + cross-chunk offset ----------------
         float run = 0.f;
-        if (g * CH < Mp) {
+        if (has_chunk) {
             for (int k = k0; k < k1; ++k) {
                 if (k < n) {
-                    const float X2 = A[(size_t)pos[k] * TP + p].x;             // log2(e) * X_k
-                    const float v = P.xi * fast_ex2(X2 + comp2[k]);            // xi exp(X - eta^2 t^2H / 2)
-                    const float d = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * W[(size_t)k * TP + p];
-                    run += d;
+                    run += W[(size_t)k * TP + p];
                     W[(size_t)k * TP + p] = run;
                 }
             }
@@ -218,7 +296,7 @@ __global__ void __launch_bounds__(NT) rbergomi_paths_kernel(RbParams P, PhiloxKe
         for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
         if (live) {
             if (g == 0) out[path] = P.S0;
-            if (g * CH < Mp) {
+            if (has_chunk) {
                 for (int k = k0; k < k1; ++k)
                     if (k < n) out[(int64_t)(k + 1) * P.ld + path] = P.S0 * fast_ex2(1.4426950408889634f * (off + W[(size_t)k * TP + p]));
             }
@@ -265,7 +343,8 @@ int launch_tp(mcp_ctx* ctx, const RbParams& P, const PhiloxKeys& K, const float2
 //   phis_k = phi_k * sqrt(2H) eta / M' * log2(e)                    (:270 pads to M' = nextPow2(n); :284 scale; :198-200 1/M')
 //   comp2_k = -0.5 eta^2 t_k^{2H} * log2(e)                         :304
 int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<float>& phis, std::vector<float>& tw,
-                        std::vector<float>& comp2, std::vector<int>& pos, int* Mp_out, int radix[4], int* n_stage) {
+                        std::vector<float>& comp2, std::vector<int>& rev, int* Mp_out, int* lgMp_out, int* lg_radix_out,
+                        int* n_stage) {
     const int M = next_pow2(n + 1), Mp = next_pow2(n);
     const double log2e = 1.4426950408889634074;
     std::vector<double> lam(n + 1);
@@ -293,14 +372,17 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<floa
     for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * pow((double)k * dt, 2.0 * H) * log2e);
     int lg = 0;
     while ((1 << lg) < Mp) ++lg;
-    int ns = 0, rem = lg;
+    int radix[8], ns = 0, rem = lg, packed = 0;
     while (rem >= 3) { radix[ns++] = 8; rem -= 3; }
     if (rem == 2) radix[ns++] = 4;
     if (rem == 1) radix[ns++] = 2;
-    for (int s = ns; s < 4; ++s) radix[s] = 1;
+    for (int s = 0; s < ns; ++s) packed |= (radix[s] == 8 ? 3 : radix[s] == 4 ? 2 : 1) << (2 * s);
     *n_stage = ns;
-    // position of output m after the DIF passes: m = s1 + R1 (s2 + R2 (s3 ...)),  pos = s1 Mp/R1 + s2 Mp/(R1 R2) + ...
-    pos.assign((size_t)Mp, 0);
+    *lg_radix_out = packed;
+    *lgMp_out = lg;
+    // storage position of output m after the DIF passes: m = s1 + R1 (s2 + R2 (s3 ...)),  pos = s1 Mp/R1 + s2 Mp/(R1 R2) + ...
+    // rev[pos] = m is what the last pass needs.
+    rev.assign((size_t)Mp, 0);
     for (int m = 0; m < Mp; ++m) {
         int rest = m, L = Mp, q = 0;
         for (int s = 0; s < ns; ++s) {
@@ -309,7 +391,7 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<floa
             q += (rest % R) * L;
             rest /= R;
         }
-        pos[m] = q;
+        rev[q] = m;
     }
     *Mp_out = Mp;
     return 0;
@@ -332,10 +414,10 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     }
 
     std::vector<float> phis, tw, comp2;
-    std::vector<int> pos;
+    std::vector<int> pos;  // rev[]: storage position -> output index
     RbParams P;
     memset(&P, 0, sizeof(P));
-    mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, phis, tw, comp2, pos, &P.Mp, P.radix, &P.n_stage);
+    mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, phis, tw, comp2, pos, &P.Mp, &P.lgMp, &P.lg_radix, &P.n_stage);
     P.S0 = (float)prm->S0;
     P.xi = (float)prm->xi;
     P.r_dt = (float)(prm->r * prm->dt);

@@ -4,8 +4,10 @@
 // (RoughVolatility.cpp:238-262): sequential, stateful and non-reproducible.  A counter-based generator has
 // no state to carry, so any (path, step) cell can be produced by any thread and results do not depend on
 // the launch geometry or the number of GPUs.  Stream layout (must match oracle/port/mcp_oracle.c):
-//   rough-vol: ctr = (g_lo, g_hi, k, 0)   -> (x0,x1) => (Zre_k, Zim_k),  (x2,x3) => (W1_k, W2_k)
-//   gbm      : ctr = (g_lo, g_hi, q, 1)   -> normals of steps 4q .. 4q+3
+//   rough-vol Z: ctr = (g_lo, g_hi, k>>1, 0) -> (x0,x1) => (Zre_k, Zim_k) for even k, (x2,x3) for odd k
+//   rough-vol W: ctr = (g_lo, g_hi, k>>2, 2) -> four real normals W_{4q..4q+3} (the single N(0,1) that the reference
+//                builds as rho W1 + sqrt(1-rho^2) W2; 3 normals per path-step instead of 4, same law)
+//   gbm        : ctr = (g_lo, g_hi, q, 1)    -> normals of steps 4q .. 4q+3
 // with g the GLOBAL path id and key = 64-bit seed.
 #pragma once
 #include <cuda_runtime.h>
@@ -38,12 +40,12 @@ static inline PhiloxKeys philox_make_keys(uint64_t seed) {
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t lo0 = MCP_PHILOX_M0 * c0, hi0 = __umulhi(MCP_PHILOX_M0, c0);
-        const uint32_t lo1 = MCP_PHILOX_M1 * c2, hi1 = __umulhi(MCP_PHILOX_M1, c2);
-        c0 = hi1 ^ c1 ^ K.k0[r];
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ K.k1[r];
-        c3 = lo0;
+        const unsigned long long p0 = (unsigned long long)MCP_PHILOX_M0 * c0;  // one IMAD.WIDE.U32 each
+        const unsigned long long p1 = (unsigned long long)MCP_PHILOX_M1 * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
+        c1 = (uint32_t)p1;
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
+        c3 = (uint32_t)p0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -54,7 +56,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float th = fmaf(__uint2float_rn(b), 1.4629180792671596e-09f, 7.314590396335798e-10f);  // 2pi * 2^-32 (b + 0.5)
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));                                  // -2 ln u1 = -2 ln2 log2 u1
+    float rad;                                                                                     // sqrt(-2 ln u1), -2 ln u1 = -2 ln2 log2 u1
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     float s, c;
     __sincosf(th, &s, &c);
     z0 = rad * c;

@@ -51,7 +51,7 @@ class _Port:
         L.orc_philox4x32_10.restype = None
         L.orc_box_muller.argtypes = [C.c_uint32, C.c_uint32, _dp, _dp]
         L.orc_box_muller.restype = None
-        L.orc_rbergomi_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_long, C.c_int, _dp]
+        L.orc_rbergomi_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_long, C.c_int, C.c_double, _dp]
         L.orc_rbergomi_draws.restype = None
         L.orc_gbm_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_long, C.c_int, _dp]
         L.orc_gbm_draws.restype = None
@@ -81,9 +81,10 @@ class _Port:
         self.L.orc_box_muller(int(a), int(b), C.byref(z0), C.byref(z1))
         return z0.value, z1.value
 
-    def rbergomi_draws(self, seed, path0, n_paths, n):
+    def rbergomi_draws(self, seed, path0, n_paths, n, rho):
+        """Native-stream normals in the reference's 4-slot order (W slots carry rho*W and sqrt(1-rho^2)*W)."""
         d = np.empty((n_paths, 4 * n), dtype=np.float64)
-        self.L.orc_rbergomi_draws(seed, path0, n_paths, n, _ptr(d, _dp))
+        self.L.orc_rbergomi_draws(seed, path0, n_paths, n, rho, _ptr(d, _dp))
         return d
 
     def gbm_draws(self, seed, path0, n_paths, n):

@@ -60,14 +60,20 @@ void orc_box_muller(uint32_t a, uint32_t b, double *z0, double *z1)
     *z1 = rad * sin(2.0 * M_PI * u2);
 }
 
-/* [new] Native stream layout, rough-vol generator: one Philox call per (global path id g, step k):
- *   ctr = (g_lo, g_hi, k, 0), key = (seed_lo, seed_hi);  (x0,x1)->(Zre_k,Zim_k), (x2,x3)->(W1_k,W2_k).
- * Written in the reference's consumption order (RoughVolatility.cpp:346-352):
- *   draws[p][2k]=Zre_k, [2k+1]=Zim_k, [2n+k]=W1_k, [3n+k]=W2_k. */
-void orc_rbergomi_draws(uint64_t seed, uint64_t path0, long n_paths, int n, double *draws)
+/* [new] Native stream layout, rough-vol generator.  g = GLOBAL path id, key = (seed_lo, seed_hi):
+ *   Z_k (complex):  x = Philox(ctr = (g_lo, g_hi, k>>1, 0));  k even: (x0,x1) -> (Zre_k, Zim_k), k odd: (x2,x3)
+ *   W_k (real)   :  x = Philox(ctr = (g_lo, g_hi, k>>2, 2));  pair (x0,x1) serves k&3 in {0,1}, (x2,x3) serves {2,3};
+ *                   within a pair the cosine branch is the even k, the sine branch the odd k.
+ * The reference mixes two independent normals, dW = rho W1 + sqrt(1-rho^2) W2 (RoughVolatility.cpp:356-358), which
+ * is again N(0,1): the native stream draws that ONE normal W_k directly (3 normals per path-step instead of 4; the
+ * law of the paths is unchanged).  For replay through the reference's 4-slot interface the draws are written in
+ * its consumption order (RoughVolatility.cpp:346-352) as
+ *   draws[p][2k]=Zre_k, [2k+1]=Zim_k, [2n+k]=rho W_k, [3n+k]=sqrt(1-rho^2) W_k      (so that rho W1 + rho_c W2 = W_k). */
+void orc_rbergomi_draws(uint64_t seed, uint64_t path0, long n_paths, int n, double rho, double *draws)
 {
     long p;
     uint32_t key[2];
+    const double rho_c = sqrt(1.0 - rho * rho);
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
     for (p = 0; p < n_paths; ++p) {
         uint64_t g = path0 + (uint64_t)p;
@@ -75,10 +81,18 @@ void orc_rbergomi_draws(uint64_t seed, uint64_t path0, long n_paths, int n, doub
         int k;
         for (k = 0; k < n; ++k) {
             uint32_t ctr[4], x[4];
-            ctr[0] = (uint32_t)g; ctr[1] = (uint32_t)(g >> 32); ctr[2] = (uint32_t)k; ctr[3] = 0u;
+            double a, b, w;
+            ctr[0] = (uint32_t)g; ctr[1] = (uint32_t)(g >> 32); ctr[2] = (uint32_t)(k >> 1); ctr[3] = 0u;
             orc_philox4x32_10(ctr, key, x);
-            orc_box_muller(x[0], x[1], &d[2 * k], &d[2 * k + 1]);
-            orc_box_muller(x[2], x[3], &d[2 * n + k], &d[3 * n + k]);
+            if (k & 1) orc_box_muller(x[2], x[3], &d[2 * k], &d[2 * k + 1]);
+            else orc_box_muller(x[0], x[1], &d[2 * k], &d[2 * k + 1]);
+            ctr[2] = (uint32_t)(k >> 2); ctr[3] = 2u;
+            orc_philox4x32_10(ctr, key, x);
+            if (k & 2) orc_box_muller(x[2], x[3], &a, &b);
+            else orc_box_muller(x[0], x[1], &a, &b);
+            w = (k & 1) ? b : a;
+            d[2 * n + k] = rho * w;
+            d[3 * n + k] = rho_c * w;
         }
     }
 }

@@ -179,7 +179,7 @@ def test_price_rbergomi_lsm_native_within_3se_of_oracle(engine, port):
     model = dict(S0=100.0, r=0.05, xi=0.04, H=0.1, eta=1.9, rho=-0.9, dt=1 / 252)
     lsm = dict(r=0.05, strike=100.0, maturity=1.0, dt=1 / 252, is_call=False, poly_order=3, carry=m.MCP_F32)
     out, gen_ms = engine.price_rbergomi_lsm(model, lsm, 1 << 15, 252, seed=2024)
-    d = port.rbergomi_draws(777, 0, 1 << 15, 252)
+    d = port.rbergomi_draws(777, 0, 1 << 15, 252, -0.9)
     paths = port.rbergomi_paths(100.0, 0.05, 0.04, 0.1, 1.9, -0.9, 1 / 252, 252, d)
     want = port.lsm(paths, 0.05, 100.0, 1.0, 1 / 252, False, 3)
     se = np.hypot(out.std_error, want["stderr"])

@@ -83,11 +83,16 @@ def test_native_philox_dump_replays_through_oracle(engine, port):
                                used.astype(np.float64))
     assert np.max(np.abs(got - want) / want) < REL_TOL
     # and the dumped normals are the documented Philox/Box-Muller stream (fp32 SFU approximations: 5e-6 abs)
-    ref_draws = port.rbergomi_draws(1234, 7, n_paths, n)
+    ref_draws = port.rbergomi_draws(1234, 7, n_paths, n, CFG2["rho"])
     check_normals(used, ref_draws)
-    # statistical sanity of the native stream
-    assert abs(used.mean()) < 5 / np.sqrt(used.size)
-    assert abs(used.std() - 1) < 5 / np.sqrt(2 * used.size)
+    # statistical sanity of the native stream: Z slots are N(0,1); the W slots carry rho*W and sqrt(1-rho^2)*W
+    z = used[:, :2 * n].astype(np.float64)
+    w = CFG2["rho"] * used[:, 2 * n:3 * n].astype(np.float64) + np.sqrt(1 - CFG2["rho"] ** 2) * used[:, 3 * n:].astype(np.float64)
+    for x in (z, w):
+        assert abs(x.mean()) < 5 / np.sqrt(x.size)
+        assert abs(x.std() - 1) < 5 / np.sqrt(2 * x.size)
+    assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5 / np.sqrt(z.size / 2)
+    assert abs(np.corrcoef(w[:, :-1].ravel(), w[:, 1:].ravel())[0, 1]) < 5 / np.sqrt(w.size)
 
 
 def test_gbm_native_dump_matches_stream_spec(engine, port):
