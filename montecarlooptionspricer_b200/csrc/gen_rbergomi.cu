@@ -41,7 +41,7 @@ struct RbParams {
     int Mp;       // DFT length = nextPow2(n)
     int lgMp;     // log2(Mp)
     int n_stage;  // DIF stages
-    int lg_radix; // 2 bits per stage: log2(radix) of stage s at bits [2s, 2s+2)
+    int lg_radix; // 3 bits per stage: log2(radix) of stage s at bits [3s, 3s+3)
     int64_t n_paths, ld;
     uint64_t path_offset;
     int64_t ld_draws;  // row stride of the slot-major draw tables
@@ -86,9 +86,35 @@ __device__ __forceinline__ void dft8(float2 (&x)[8]) {
     x[1] = b0; x[3] = b1; x[5] = b2; x[7] = b3;
 }
 
+// forward 16-point DFT as 4 x 4:  q = q1 + 4 q2,  s = 4 s1 + s2,
+//   w16^{qs} = w4^{q2 s2} * w16^{q1 s2} * w4^{q1 s1}.  Output X[4 s1 + s2] is left in x[4 s2 + s1].
+__device__ __forceinline__ void dft16_transposed(float2 (&x)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+#pragma unroll
+    for (int q1 = 0; q1 < 4; ++q1) dft4(x[q1], x[q1 + 4], x[q1 + 8], x[q1 + 12]);  // x[q1 + 4 s2] = Y[q1][s2]
+    // twiddles w16^{q1 s2}
+    x[5] = cmul(x[5], make_float2(c1, -s1));                             // e = 1
+    x[9] = make_float2((x[9].x + x[9].y) * h, (x[9].y - x[9].x) * h);    // e = 2
+    x[13] = cmul(x[13], make_float2(s1, -c1));                           // e = 3
+    x[6] = make_float2((x[6].x + x[6].y) * h, (x[6].y - x[6].x) * h);    // e = 2
+    x[10] = mul_mi(x[10]);                                               // e = 4
+    x[14] = make_float2((x[14].y - x[14].x) * h, -(x[14].x + x[14].y) * h);  // e = 6
+    x[7] = cmul(x[7], make_float2(s1, -c1));                             // e = 3
+    x[11] = make_float2((x[11].y - x[11].x) * h, -(x[11].x + x[11].y) * h);  // e = 6
+    x[15] = cmul(x[15], make_float2(-c1, s1));                           // e = 9
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) dft4(x[4 * s2], x[4 * s2 + 1], x[4 * s2 + 2], x[4 * s2 + 3]);
+}
+
+// index in x[] that holds output s after dftR
+template <int R>
+__device__ __forceinline__ constexpr int out_slot(int s) { return R == 16 ? 4 * (s & 3) + (s >> 2) : s; }
+
 template <int R>
 __device__ __forceinline__ void dftR(float2 (&x)[R]) {
-    if constexpr (R == 8) {
+    if constexpr (R == 16) {
+        dft16_transposed(x);
+    } else if constexpr (R == 8) {
         dft8(x);
     } else if constexpr (R == 4) {
         dft4(x[0], x[1], x[2], x[3]);
@@ -115,10 +141,10 @@ __device__ __forceinline__ void dif_pass(float2* __restrict__ A, const float2* _
         if (lgS > 0) {
             const int jt = j << (lgMp - lgL);
 #pragma unroll
-            for (int s = 1; s < R; ++s) x[s] = cmul(x[s], tw[(jt * s) & (Mp - 1)]);
+            for (int s = 1; s < R; ++s) x[out_slot<R>(s)] = cmul(x[out_slot<R>(s)], tw[(jt * s) & (Mp - 1)]);
         }
 #pragma unroll
-        for (int s = 0; s < R; ++s) a[(size_t)(s << lgS) * TP] = x[s];
+        for (int s = 0; s < R; ++s) a[(size_t)(s << lgS) * TP] = x[out_slot<R>(s)];
     }
 }
 
@@ -140,7 +166,7 @@ __device__ __forceinline__ void last_pass(const float2* __restrict__ A, float* _
         for (int s = 0; s < R; ++s) {
             const int m = rev[(bf << LGR) + s];
             if (m < P.n) {
-                const float v = P.xi * fast_ex2(x[s].x + comp2[m]);
+                const float v = P.xi * fast_ex2(x[out_slot<R>(s)].x + comp2[m]);
                 float* w = W + (size_t)m * TP + p;
                 *w = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * *w;
             }
@@ -258,13 +284,15 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
         {
             int lgL = P.lgMp;
             for (int s = 0; s < P.n_stage; ++s) {
-                const int lgR = (P.lg_radix >> (2 * s)) & 3;
+                const int lgR = (P.lg_radix >> (3 * s)) & 7;
                 if (s + 1 < P.n_stage) {
-                    if (lgR == 3) dif_pass<3, TP>(A, tw, P.lgMp, lgL, g, p);
+                    if (lgR == 4) dif_pass<4, TP>(A, tw, P.lgMp, lgL, g, p);
+                    else if (lgR == 3) dif_pass<3, TP>(A, tw, P.lgMp, lgL, g, p);
                     else if (lgR == 2) dif_pass<2, TP>(A, tw, P.lgMp, lgL, g, p);
                     else dif_pass<1, TP>(A, tw, P.lgMp, lgL, g, p);
                 } else {
-                    if (lgR == 3) last_pass<3, TP>(A, W, rev, comp2, P, g, p);
+                    if (lgR == 4) last_pass<4, TP>(A, W, rev, comp2, P, g, p);
+                    else if (lgR == 3) last_pass<3, TP>(A, W, rev, comp2, P, g, p);
                     else if (lgR == 2) last_pass<2, TP>(A, W, rev, comp2, P, g, p);
                     else last_pass<1, TP>(A, W, rev, comp2, P, g, p);
                 }
@@ -283,11 +311,12 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
         // ---- phase 3: log-space prefix sum over time: chunk-local scan + cross-chunk offset ----------------
         float run = 0.f;
         if (has_chunk) {
-            for (int k = k0; k < k1; ++k) {
-                if (k < n) {
-                    run += W[(size_t)k * TP + p];
-                    W[(size_t)k * TP + p] = run;
-                }
+            float* w = W + (size_t)k0 * TP + p;
+            const int kend = min(k1, n);
+#pragma unroll 4
+            for (int k = k0; k < kend; ++k, w += TP) {
+                run += *w;
+                *w = run;
             }
         }
         tot[g * TP + p] = run;
@@ -297,8 +326,11 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
         if (live) {
             if (g == 0) out[path] = P.S0;
             if (has_chunk) {
-                for (int k = k0; k < k1; ++k)
-                    if (k < n) out[(int64_t)(k + 1) * P.ld + path] = P.S0 * fast_ex2(1.4426950408889634f * (off + W[(size_t)k * TP + p]));
+                float* o = out + (int64_t)(k0 + 1) * P.ld + path;
+                const float* w = W + (size_t)k0 * TP + p;
+                const int kend = min(k1, n);
+#pragma unroll 4
+                for (int k = k0; k < kend; ++k, o += P.ld, w += TP) *o = P.S0 * fast_ex2(1.4426950408889634f * (off + *w));
             }
         }
         __syncthreads();  // A / W / tot are rewritten by the next tile
@@ -373,10 +405,11 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<floa
     int lg = 0;
     while ((1 << lg) < Mp) ++lg;
     int radix[8], ns = 0, rem = lg, packed = 0;
-    while (rem >= 3) { radix[ns++] = 8; rem -= 3; }
+    while (rem >= 4) { radix[ns++] = 16; rem -= 4; }
+    if (rem == 3) radix[ns++] = 8;
     if (rem == 2) radix[ns++] = 4;
     if (rem == 1) radix[ns++] = 2;
-    for (int s = 0; s < ns; ++s) packed |= (radix[s] == 8 ? 3 : radix[s] == 4 ? 2 : 1) << (2 * s);
+    for (int s = 0; s < ns; ++s) packed |= (radix[s] == 16 ? 4 : radix[s] == 8 ? 3 : radix[s] == 4 ? 2 : 1) << (3 * s);
     *n_stage = ns;
     *lg_radix_out = packed;
     *lgMp_out = lg;

@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: libmcp_b200.so loads, exports every symbol include/mcp_b200.h declares, the
+ctypes table matches the header, and without a GPU every entry point fails LOUDLY (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mcp_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from montecarlooptionspricer_b200 import build
+    lib = build.build_cuda()
+    assert os.path.exists(lib)
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (mcp_[a-z0-9_]+)", out))
+    syms = header_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f"declared in include/mcp_b200.h but not exported: {missing}"
+
+
+def test_ctypes_table_covers_the_header():
+    from montecarlooptionspricer_b200 import _capi
+    L = _capi.lib()  # resolves every name in SIGNATURES or raises
+    assert L.mcp_abi_version() == 1
+    assert sorted(_capi.SIGNATURES) == header_symbols()
+
+
+def test_sm100a_code_is_what_ships():
+    from montecarlooptionspricer_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build_cuda()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def _has_gpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU ") > 0
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_means_loud_failure_not_fallback():
+    import montecarlooptionspricer_b200 as m
+    with pytest.raises(m.McpError) as e:
+        m.Engine(0)
+    assert e.value.code == m.capi.MCP_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(m.McpError):
+        m.LSM().PredictOptionPrice([[100.0, 101.0], [100.0, 99.0]], 0.05, 100.0, 1.0, 0.5, False, 1)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "montecarlooptionspricer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libmcp_oracle" not in src and "libmcp_ref" not in src and "oracle/" not in src.replace("oracle/port/mcp_oracle.c", ""), f
+
+
+def test_reference_plugin_error_message_without_device():
+    """Empty input is rejected on the host with the reference's message before any device work."""
+    import montecarlooptionspricer_b200 as m
+    with pytest.raises(RuntimeError, match="LSM::PredictOptionPrice: Empty pricePaths."):
+        m.LSM(engine=None).PredictOptionPrice([], 0.05, 100.0, 1.0, 0.02, False, 2)
