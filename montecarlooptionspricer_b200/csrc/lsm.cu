@@ -53,6 +53,7 @@ struct LsmDev {  // pointers into ctx scratch
     double* moments;  // [MOM_LD]
     double* fin;      // [4]      sum V0, sum V0^2, n
     int* kind;        // [M]
+    unsigned int* counter;  // CTA completion ticket for the last-block epilogue (self-resetting)
 };
 
 struct SweepArgs {
@@ -66,7 +67,8 @@ struct SweepArgs {
     int j;           // step being decided
     int terminal;    // j == M-1: V = payoff
     int do_moments;  // accumulate moments of step j-1
-    int do_final;    // j == 0: accumulate sum V, sum V^2
+    int do_final;    // j == 0: accumulate sum V0
+    int solve_here;  // single GPU: the last CTA to finish also solves step j-1 (no extra launches)
 };
 
 __device__ __forceinline__ double payoff_fn(int is_call, double S, double K) {  // include/core/common.h:8-14
@@ -98,6 +100,10 @@ __device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NV], doubl
         partial_row[threadIdx.x] = s;
     }
 }
+
+struct SweepArgs;
+template <int NV, int P>
+__device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)[NV]);
 
 // Exact float -> double widening on the integer pipe (the F2F conversion unit is quarter rate and was the top
 // stall of the first sweep kernel: 44% of samples).  Sub-normals flush to zero (prices and option values never
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_kernel(SweepArgs a) {
         }
     }
     if (a.do_moments) acc[0] = (double)cnt;
-    if (a.do_moments || a.do_final) block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+    if (a.do_moments || a.do_final) sweep_epilogue<NV, P>(a, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -320,116 +326,190 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast_kernel(SweepArgs a) 
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] += (double)la[k];
-    if (a.do_moments || a.do_final) block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+    if (a.do_moments || a.do_final) sweep_epilogue<NV, P>(a, acc);
 }
 
 // Sum the per-CTA partial rows in a fixed order -> out[0..nv).
 __global__ void __launch_bounds__(256) lsm_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
-    __shared__ double red[256];
-    for (int k = 0; k < nv; ++k) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * MOM_LD + k];
-        red[threadIdx.x] = s;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[k] = red[0];
-        __syncthreads();
+    __shared__ double red[8][32];
+    const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    double s = 0.0;
+    if (k < nv)
+        for (int b = grp; b < nblocks; b += 8) s += partial[(int64_t)b * MOM_LD + k];
+    red[grp][k] = s;
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[g][threadIdx.x];
+        out[threadIdx.x] = t;
     }
 }
 
-// Solve the normal equations of one step from the (globally reduced) moments -> coef row.
-//   G[a][b] = s[a+b], rhs[a] = t[a].  Diagonal equilibration, Cholesky when safely positive definite, else
-//   Jacobi eigen-decomposition with pseudo-inverse (projection onto the realised column space).
-__global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* __restrict__ coef_row) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int n = p + 1;
-    double G[MAXP + 1][MAXP + 1], rhs[MAXP + 1], d[MAXP + 1], z[MAXP + 1];
+// Rank-revealing fallback: cyclic Jacobi on the equilibrated Gram matrix, pseudo-inverse with a relative cut
+// (projection of y onto the realised column space == what the reference's min-norm SVD solve evaluates to at the
+// regression points, LSMPricer.cpp:76-85).  Rare (j = 0 in the money, fewer ITM paths than basis functions).
+__device__ __noinline__ void solve_fallback_jacobi(double* G /*[n][MAXP+1], destroyed*/, const double* rhs, int n, double* z) {
+    double Q[MAXP + 1][MAXP + 1];
+    auto g = [&](int a, int b) -> double& { return G[a * (MAXP + 1) + b]; };
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) Q[a][b] = a == b ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0;
+        for (int a = 0; a < n; ++a)
+            for (int b = a + 1; b < n; ++b) off += g(a, b) * g(a, b);
+        if (off < 1e-60) break;
+        for (int pp = 0; pp < n - 1; ++pp)
+            for (int q = pp + 1; q < n; ++q) {
+                const double apq = g(pp, q);
+                if (apq == 0.0) continue;
+                const double theta = (g(q, q) - g(pp, pp)) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < n; ++k) {
+                    const double gkp = g(k, pp), gkq = g(k, q);
+                    g(k, pp) = cs * gkp - sn * gkq;
+                    g(k, q) = sn * gkp + cs * gkq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double gpk = g(pp, k), gqk = g(q, k);
+                    g(pp, k) = cs * gpk - sn * gqk;
+                    g(q, k) = sn * gpk + cs * gqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double qkp = Q[k][pp], qkq = Q[k][q];
+                    Q[k][pp] = cs * qkp - sn * qkq;
+                    Q[k][q] = sn * qkp + cs * qkq;
+                }
+            }
+    }
+    double lmax = 0.0;
+    for (int a = 0; a < n; ++a) lmax = fmax(lmax, g(a, a));
+    const double thr = lmax * (double)n * 64.0 * 2.220446049250313e-16;
+    for (int a = 0; a < n; ++a) z[a] = 0.0;
+    for (int e = 0; e < n; ++e) {
+        if (g(e, e) > thr) {
+            double proj = 0.0;
+            for (int a = 0; a < n; ++a) proj += Q[a][e] * rhs[a];
+            proj /= g(e, e);
+            for (int a = 0; a < n; ++a) z[a] += Q[a][e] * proj;
+        }
+    }
+}
+
+// Solve the normal equations of one step from the (globally reduced) moments -> coef row (one thread).
+//   G[a][b] = s[a+b], rhs[a] = t[a].  Diagonal equilibration; Cholesky when safely positive definite (unrolled,
+//   in registers), else the Jacobi fallback above.
+template <int P>
+__device__ __forceinline__ void solve_normal_equations(const double* mom, double* __restrict__ coef_row) {
+    constexpr int n = P + 1;
+    double G[n][n], rhs[n], d[n], z[n], L[n][n];
+#pragma unroll
     for (int k = 0; k < COEF_LD; ++k) coef_row[k] = 0.0;
     if (!(mom[0] > 0.0)) return;  // no in-the-money path at this step (LSMPricer.cpp:60)
+#pragma unroll
+    for (int a = 0; a < n; ++a) d[a] = mom[2 * a] > 0.0 ? rsqrt(mom[2 * a]) : 0.0;
+#pragma unroll
     for (int a = 0; a < n; ++a) {
-        d[a] = mom[2 * a] > 0.0 ? 1.0 / sqrt(mom[2 * a]) : 0.0;
-    }
-    for (int a = 0; a < n; ++a) {
+#pragma unroll
         for (int b = 0; b < n; ++b) G[a][b] = mom[a + b] * d[a] * d[b];
-        rhs[a] = mom[2 * p + 1 + a] * d[a];
+        rhs[a] = mom[2 * P + 1 + a] * d[a];
     }
-    // --- Cholesky attempt ---
-    double L[MAXP + 1][MAXP + 1];
     bool ok = true;
-    for (int k = 0; k < n && ok; ++k) {
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
         double piv = G[k][k];
+#pragma unroll
         for (int m = 0; m < k; ++m) piv -= L[k][m] * L[k][m];
-        if (!(piv > 1e-10)) { ok = false; break; }
-        const double lkk = sqrt(piv);
-        L[k][k] = lkk;
+        ok = ok && (piv > 1e-10);
+        const double inv = rsqrt(ok ? piv : 1.0);
+        L[k][k] = inv;  // store 1/l_kk
+#pragma unroll
         for (int i = k + 1; i < n; ++i) {
-            double s = G[i][k];
-            for (int m = 0; m < k; ++m) s -= L[i][m] * L[k][m];
-            L[i][k] = s / lkk;
+            double sacc = G[i][k];
+#pragma unroll
+            for (int m = 0; m < k; ++m) sacc -= L[i][m] * L[k][m];
+            L[i][k] = sacc * inv;
         }
     }
     if (ok) {
+#pragma unroll
         for (int i = 0; i < n; ++i) {
-            double s = rhs[i];
-            for (int m = 0; m < i; ++m) s -= L[i][m] * z[m];
-            z[i] = s / L[i][i];
+            double sacc = rhs[i];
+#pragma unroll
+            for (int m = 0; m < i; ++m) sacc -= L[i][m] * z[m];
+            z[i] = sacc * L[i][i];
         }
+#pragma unroll
         for (int i = n - 1; i >= 0; --i) {
-            double s = z[i];
-            for (int m = i + 1; m < n; ++m) s -= L[m][i] * z[m];
-            z[i] = s / L[i][i];
+            double sacc = z[i];
+#pragma unroll
+            for (int m = i + 1; m < n; ++m) sacc -= L[m][i] * z[m];
+            z[i] = sacc * L[i][i];
         }
     } else {
-        // --- cyclic Jacobi on the symmetric G; Q accumulates eigenvectors (columns) ---
-        double Q[MAXP + 1][MAXP + 1];
-        for (int a = 0; a < n; ++a)
-            for (int b = 0; b < n; ++b) Q[a][b] = a == b ? 1.0 : 0.0;
-        for (int sweep = 0; sweep < 40; ++sweep) {
-            double off = 0.0;
-            for (int a = 0; a < n; ++a)
-                for (int b = a + 1; b < n; ++b) off += G[a][b] * G[a][b];
-            if (off < 1e-60) break;
-            for (int pp = 0; pp < n - 1; ++pp)
-                for (int q = pp + 1; q < n; ++q) {
-                    const double apq = G[pp][q];
-                    if (apq == 0.0) continue;
-                    const double theta = (G[q][q] - G[pp][pp]) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
-                    for (int k = 0; k < n; ++k) {
-                        const double gkp = G[k][pp], gkq = G[k][q];
-                        G[k][pp] = cs * gkp - sn * gkq;
-                        G[k][q] = sn * gkp + cs * gkq;
-                    }
-                    for (int k = 0; k < n; ++k) {
-                        const double gpk = G[pp][k], gqk = G[q][k];
-                        G[pp][k] = cs * gpk - sn * gqk;
-                        G[q][k] = sn * gpk + cs * gqk;
-                    }
-                    for (int k = 0; k < n; ++k) {
-                        const double qkp = Q[k][pp], qkq = Q[k][q];
-                        Q[k][pp] = cs * qkp - sn * qkq;
-                        Q[k][q] = sn * qkp + cs * qkq;
-                    }
-                }
+        double Gf[(MAXP + 1) * (MAXP + 1)], rf[MAXP + 1], zf[MAXP + 1];
+        for (int a = 0; a < n; ++a) {
+            for (int b = 0; b < n; ++b) Gf[a * (MAXP + 1) + b] = G[a][b];
+            rf[a] = rhs[a];
         }
-        double lmax = 0.0;
-        for (int a = 0; a < n; ++a) lmax = fmax(lmax, G[a][a]);
-        const double thr = lmax * (double)n * 64.0 * 2.220446049250313e-16;
-        for (int a = 0; a < n; ++a) z[a] = 0.0;
-        for (int e = 0; e < n; ++e) {
-            if (G[e][e] > thr) {
-                double proj = 0.0;
-                for (int a = 0; a < n; ++a) proj += Q[a][e] * rhs[a];
-                proj /= G[e][e];
-                for (int a = 0; a < n; ++a) z[a] += Q[a][e] * proj;
-            }
-        }
+        solve_fallback_jacobi(Gf, rf, n, zf);
+        for (int a = 0; a < n; ++a) z[a] = zf[a];
     }
+#pragma unroll
     for (int a = 0; a < n; ++a) coef_row[a] = z[a] * d[a];
+}
+
+__device__ __noinline__ void solve_dispatch(const double* mom, int p, double* coef_row) {
+    switch (p) {
+        case 0: solve_normal_equations<0>(mom, coef_row); break;
+        case 1: solve_normal_equations<1>(mom, coef_row); break;
+        case 2: solve_normal_equations<2>(mom, coef_row); break;
+        case 3: solve_normal_equations<3>(mom, coef_row); break;
+        case 4: solve_normal_equations<4>(mom, coef_row); break;
+        case 5: solve_normal_equations<5>(mom, coef_row); break;
+        default: solve_normal_equations<6>(mom, coef_row); break;
+    }
+}
+
+// Multi-GPU path: after the NCCL all-reduce of the moments every rank solves the same tiny system.
+__global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* __restrict__ coef_row) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) solve_dispatch(mom, p, coef_row);
+}
+
+// Epilogue of a sweep launch: per-CTA partial row, then the LAST CTA to finish (completion ticket) folds all rows
+// in a fixed order -- bitwise reproducible whichever CTA is last -- into `moments` (or the running sum of V0) and,
+// on a single GPU, solves step j-1 right here, so one time step is exactly one kernel launch.
+template <int NV, int P>
+__device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)[NV]) {
+    __shared__ double red[8][32];
+    __shared__ bool is_last;
+    block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(a.d.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    double s = 0.0;
+    if (k < NV)
+        for (int b = grp; b < (int)gridDim.x; b += LSM_NT / 32) s += __ldcg(a.d.partial + (int64_t)b * MOM_LD + k);
+    red[grp][k] = s;
+    __syncthreads();
+    double* out = a.do_final ? a.d.fin : a.d.moments;
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < LSM_NT / 32; ++g) t += red[g][threadIdx.x];
+        red[0][threadIdx.x] = t;
+        if (!a.do_final || threadIdx.x == 0) out[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.d.counter = 0u;
+        if (a.do_moments && a.solve_here) solve_normal_equations<P>(&red[0][0], a.d.coef + (int64_t)(a.j - 1) * COEF_LD);
+    }
 }
 
 // Sample statistics for the standardisation: CTA j sums cnt / S / S^2 over the in-the-money prices of the
@@ -593,7 +673,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_coef = take((size_t)M * COEF_LD * 8), o_mu = take((size_t)M * 8), o_is = take((size_t)M * 8);
     const size_t o_ssum = take((size_t)M * 4 * 8), o_part = take((size_t)grid * MOM_LD * 8), o_mom = take(MOM_LD * 8);
-    const size_t o_fin = take(4 * 8), o_kind = take((size_t)M * 4);
+    const size_t o_fin = take(4 * 8), o_kind = take((size_t)M * 4), o_cnt = take(4);
     MCP_TRY(mcp_scratch_reserve(ctx, off));
     const size_t v_bytes = (size_t)mcp_round_up(N, 128) * csz;
     const size_t tau_bytes = first_exercise ? (size_t)mcp_round_up(N, 128) * 4 : 0;
@@ -602,7 +682,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     unsigned char* sb = (unsigned char*)ctx->scratch;
     LsmDev d;
     d.coef = (double*)(sb + o_coef); d.mu = (double*)(sb + o_mu); d.inv_s = (double*)(sb + o_is); d.ssum = (double*)(sb + o_ssum);
-    d.partial = (double*)(sb + o_part); d.moments = (double*)(sb + o_mom); d.fin = (double*)(sb + o_fin); d.kind = (int*)(sb + o_kind);
+    d.partial = (double*)(sb + o_part); d.moments = (double*)(sb + o_mom); d.fin = (double*)(sb + o_fin); d.kind = (int*)(sb + o_kind); d.counter = (unsigned int*)(sb + o_cnt);
     void* dV = ctx->carry;
     int32_t* dTau = first_exercise ? (int32_t*)((unsigned char*)ctx->carry + v_bytes) : nullptr;
     double* dV0 = v0 ? (double*)((unsigned char*)ctx->carry + v_bytes + tau_bytes) : nullptr;
@@ -616,6 +696,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     MCP_CUDA(ctx, cudaMemcpyAsync(d.kind, kind.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
     MCP_CUDA(ctx, cudaMemsetAsync(d.coef, 0, (size_t)M * COEF_LD * 8, st));
+    MCP_CUDA(ctx, cudaMemsetAsync(d.counter, 0, 4, st));
 
     // ---- standardisation tables from a fixed leading sample of this rank's paths (summed over ranks) ----
     const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
@@ -635,6 +716,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     memset(&a, 0, sizeof(a));
     a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
     a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
+    a.solve_here = (ctx->nranks <= 1 || !ctx->comm) ? 1 : 0;
     const int nm = 3 * p + 2;
     for (int j = M - 1; j >= 0; --j) {
         a.j = j;
@@ -645,18 +727,14 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
         MCP_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j + 1), st);
-        if (a.do_moments) {
-            lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, nm, d.moments);
-            MCP_LAUNCH_CHECK(ctx);
+        if (a.do_moments && !a.solve_here) {  // multi-GPU: global moments, then every rank solves the same system
             MCP_TRY(mcp_allreduce_f64(ctx, d.moments, nm));
             lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD);
             MCP_LAUNCH_CHECK(ctx);
         }
     }
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
-    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, 1, d.fin);
-    MCP_LAUNCH_CHECK(ctx);
-    double fin[3] = {0, 0, 0};
+    double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
     const double nloc = (double)N;
     MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
     MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below
