@@ -15,6 +15,11 @@
  *   mcp_lsm_price               LSM::PredictOptionPrice                     include/models/LSMPricer.h:8-14
  *                               (body src/models/LSMPricer.cpp:19-102)
  *   mcp_lsm_price_host_rows     the same call, bound directly to host rows  src/core/PredictionGen.cpp:790
+ *   mcp_estimate_rbergomi_params  RoughVolatility::estimateXi/H/Eta/Rho     src/models/RoughVolatility.cpp:72-169, :324-331
+ *   mcp_generate_stock_price_paths  GenerateStockPricePaths, exact call shape  src/core/PredictionGen.cpp:736-737
+ *   mcp_asymptotic_price        AsymptoticAnalysis::PredictOptionPrice      include/models/AsymptoticAnalysisPricer.h:8-15
+ *   mcp_martingale_price        MartingaleOptimization::PredictOptionPrice  include/models/MartingaleOptimizationPricer.h:10-18
+ *   mcp_branching_price         BranchingProcesses::PredictOptionPrice      include/models/BranchingProcessPricer.h:8-16
  *
  * Conventions: plain pointers and sizes only; caller allocates every output; no ownership transfer; no
  * exceptions cross the boundary; every function returns an int status (0 = ok, negative = error class) and
@@ -89,6 +94,7 @@ int mcp_pathset_info(const mcp_pathset *ps, int64_t *n_paths, int *n_steps, int6
 int mcp_pathset_upload_f64(mcp_pathset *ps, const double *host, int64_t ld_host);
 int mcp_pathset_upload_rows_f64(mcp_pathset *ps, const double *const *rows); /* vector<vector<double>> rows */
 int mcp_pathset_download_f64(const mcp_pathset *ps, double *host, int64_t ld_host);
+int mcp_pathset_download_rows_f64(const mcp_pathset *ps, double *const *rows); /* into vector<vector<double>> rows */
 /* exact device values, time-major [step][path] */
 int mcp_pathset_download_timemajor_f32(const mcp_pathset *ps, float *host, int64_t ld_host);
 
@@ -150,6 +156,30 @@ int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_p
 int mcp_price_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *model, const mcp_lsm_params *lsm,
                            int64_t n_paths, int n_steps, uint64_t seed, uint64_t path_offset,
                            mcp_lsm_result *res, float *gen_ms);
+
+/* ------------------------------------------------------------- exact-signature generator
+ * Host estimators of the reference (pure host arithmetic, no device needed): xi = var(logret)/dt, H = DFA slope
+ * (unclamped), eta = 2 std(logret), rho = corr(ret, ret^2) or -0.3 when positive, r = 0.04, dt = 1/252,
+ * S0 = hist[n-1].  MCP_ERR_DOMAIN + "Historical prices vector too small." for n_hist < 2 (RoughVolatility.cpp:317-319). */
+int mcp_estimate_rbergomi_params(const double *hist, int64_t n_hist, mcp_rbergomi_params *out);
+/* rows[path][0..forward_steps] (caller-allocated) = GenerateStockPricePaths(hist, forward_steps, path_num) with native
+ * Philox normals keyed by (seed, path_offset + path). */
+int mcp_generate_stock_price_paths(mcp_ctx *ctx, const double *hist, int64_t n_hist, int forward_steps, int path_num,
+                                   uint64_t seed, uint64_t path_offset, double *const *rows);
+
+/* ------------------------------------------------------------------- the other three plugins
+ * Same arguments as the reference methods after `pricePaths`; with a communicator the sums are global. */
+int mcp_asymptotic_price(mcp_ctx *ctx, const mcp_pathset *ps, double r, double strike, double maturity, double dt,
+                         int is_call, double sigma, double dividend, double *price);
+int mcp_martingale_price(mcp_ctx *ctx, const mcp_pathset *ps, double r, double strike, double maturity, double dt,
+                         int is_call, int poly_order, int max_iterations, double *price, double *primal /*nullable*/,
+                         double *dual /*nullable*/);
+/* exercise_times must be strictly increasing.  The upper bound resamples paths with Philox (seed, path_offset) or,
+ * when injected_rp != NULL, with the caller's indices [visited exercise date][path][branch] (parity runs). */
+int mcp_branching_price(mcp_ctx *ctx, const mcp_pathset *ps, double r, double strike, double maturity, double dt,
+                        int is_call, int num_branches, const int *exercise_times, int n_exercise, uint64_t seed,
+                        uint64_t path_offset, const int32_t *injected_rp, double *price, double *lower /*nullable*/,
+                        double *upper /*nullable*/);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@ plugin interface plus marshalling; importing it does not require a GPU, calling 
 from . import _capi as capi
 from ._capi import (MCP_BASIS_LAGUERRE, MCP_BASIS_MONOMIAL, MCP_F32, MCP_F64, McpError)
 from .engine import Engine, LsmOutput, PathSet
-from .pricers import LSM, default_engine
+from .pricers import (LSM, AsymptoticAnalysis, BranchingProcesses, MartingaleOptimization, RoughVolatility,
+                      default_engine)
 
-__all__ = ["capi", "Engine", "PathSet", "LsmOutput", "LSM", "default_engine", "McpError", "MCP_F32", "MCP_F64",
+__all__ = ["capi", "Engine", "PathSet", "LsmOutput", "LSM", "RoughVolatility", "MartingaleOptimization", "BranchingProcesses", "AsymptoticAnalysis",
+           "default_engine", "McpError", "MCP_F32", "MCP_F64",
            "MCP_BASIS_MONOMIAL", "MCP_BASIS_LAGUERRE"]

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mcp_pathset_upload_f64": (C.c_int, [_vp, _dp, C.c_int64]),
     "mcp_pathset_upload_rows_f64": (C.c_int, [_vp, C.POINTER(_dp)]),
     "mcp_pathset_download_f64": (C.c_int, [_vp, _dp, C.c_int64]),
+    "mcp_pathset_download_rows_f64": (C.c_int, [_vp, C.POINTER(_dp)]),
     "mcp_pathset_download_timemajor_f32": (C.c_int, [_vp, _fp, C.c_int64]),
     "mcp_gen_rbergomi": (C.c_int, [_vp, _vp, C.POINTER(RbergomiParams), C.c_uint64, C.c_uint64, _fp, _fp]),
     "mcp_gen_gbm": (C.c_int, [_vp, _vp, C.POINTER(GbmParams), C.c_uint64, C.c_uint64, _fp, _fp]),
@@ -76,6 +77,15 @@ SIGNATURES = {
                                           C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "mcp_price_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), C.c_int64, C.c_int,
                                          C.c_uint64, C.c_uint64, C.POINTER(LsmResult), _fp]),
+    "mcp_estimate_rbergomi_params": (C.c_int, [_dp, C.c_int64, C.POINTER(RbergomiParams)]),
+    "mcp_generate_stock_price_paths": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                                 C.POINTER(_dp)]),
+    "mcp_asymptotic_price": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_double, _dp]),
+    "mcp_martingale_price": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                       C.c_int, _dp, _dp, _dp]),
+    "mcp_branching_price": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint64, _ip, _dp, _dp, _dp]),
 }
 
 _lib = None

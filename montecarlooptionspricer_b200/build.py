@@ -19,6 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "libmcp_b200.so")
 PLUGINS = os.path.join(PKG, "libmcp_b200_plugins.so")
+DEMO = os.path.join(HOST, "plugin_rows_demo")
 
 CU_SOURCES = ["ctx.cu", "pathset.cu", "gen_rbergomi.cu", "gen_gbm.cu", "lsm.cu", "pricers.cu", "estimators.cu"]
 NVCC_FLAGS = [
@@ -56,18 +57,21 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_plugins(force: bool = False) -> str:
-    srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")] if os.path.isdir(HOST) else []
-    if not srcs:
+    """C++ host plugin classes (reference signatures) over the C ABI + the PredictionGen-shaped demo caller."""
+    src = os.path.join(HOST, "mcp_plugins.cpp")
+    if not os.path.exists(src):
         return ""
-    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith((".h", ".hpp"))] + [LIB]
-    if not force and _newer(PLUGINS, deps):
-        return PLUGINS
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST] + srcs + [
-        "-o", PLUGINS, "-L", PKG, "-lmcp_b200", "-Wl,-rpath,$ORIGIN"]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.run(cmd, check=True, env=env)
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", HOST]
+    if force or not _newer(PLUGINS, [src, os.path.join(HOST, "mcp_plugins.hpp"), os.path.join(ROOT, "include", "mcp_b200.h"), LIB]):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", *inc, src, "-o", PLUGINS, "-L", PKG, "-lmcp_b200",
+                        "-Wl,-rpath,$ORIGIN"], check=True, env=env)
+    demo_src = os.path.join(HOST, "plugin_rows_demo.cpp")
+    if os.path.exists(demo_src) and (force or not _newer(DEMO, [demo_src, PLUGINS])):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wall", *inc, demo_src, "-o", DEMO, "-L", PKG, "-lmcp_b200_plugins",
+                        "-lmcp_b200", "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
     return PLUGINS
 
 

@@ -6,6 +6,8 @@
 // std::vector<std::vector<double>> (RoughVolatility.cpp:344); LSM walks it column-wise (LSMPricer.cpp:51-94),
 // one cache line per element.  The movers below transpose through a padded shared-memory tile so both the
 // host-layout side and the slab side are accessed coalesced.
+#include <string.h>
+
 #include "common.cuh"
 #include "transpose.cuh"
 
@@ -133,6 +135,30 @@ int mcp_pathset_download_f64(const mcp_pathset* ps, double* host, int64_t ld_hos
         MCP_CUDA(ctx, cudaMemcpy2DAsync(host + p0 * ld_host, (size_t)ld_host * 8, stage, (size_t)cols * 8, (size_t)cols * 8,
                                         (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MCP_OK;
+}
+
+int mcp_pathset_download_rows_f64(const mcp_pathset* ps, double* const* rows) {
+    if (!ps || !rows) return MCP_ERR_INVALID;
+    mcp_ctx* ctx = ps->ctx;
+    const int cols = ps->n_steps + 1;
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t pc = chunk_paths(ps);
+    MCP_TRY(mcp_scratch_reserve(ctx, (size_t)pc * cols * 8));
+    MCP_TRY(mcp_pinned_reserve(ctx, (size_t)pc * cols * 8));
+    for (int64_t p0 = 0; p0 < ps->n_paths; p0 += pc) {
+        const int64_t n = (ps->n_paths - p0 < pc) ? ps->n_paths - p0 : pc;
+        double* stage = (double*)ctx->scratch;
+        if (ps->dtype == MCP_F32)
+            mcp_launch_transpose<float, double>(ctx->stream, (const float*)ps->data + p0, ps->ld, cols, n, stage, cols);
+        else
+            mcp_launch_transpose<double, double>(ctx->stream, (const double*)ps->data + p0, ps->ld, cols, n, stage, cols);
+        MCP_LAUNCH_CHECK(ctx);
+        double* pin = (double*)ctx->pinned;
+        MCP_CUDA(ctx, cudaMemcpyAsync(pin, stage, (size_t)n * cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < n; ++i) memcpy(rows[p0 + i], pin + i * cols, (size_t)cols * 8);
     }
     return MCP_OK;
 }

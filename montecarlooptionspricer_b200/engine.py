@@ -189,6 +189,56 @@ class Engine:
                                                   poly_order, C.byref(px)))
         return px.value
 
+    # -- the other three plugins ------------------------------------------------------
+    def asymptotic_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, sigma, dividend) -> float:
+        px = C.c_double()
+        self._chk(self._L.mcp_asymptotic_price(self._h, ps._h if ps is not None else None, r, strike, maturity, dt,
+                                               int(bool(is_call)), sigma, dividend, C.byref(px)))
+        return px.value
+
+    def martingale_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, poly_order, max_iterations: int = 5,
+                         want_bounds: bool = False):
+        px, lo, up = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self._L.mcp_martingale_price(self._h, ps._h if ps is not None else None, r, strike, maturity, dt,
+                                               int(bool(is_call)), poly_order, max_iterations, C.byref(px), C.byref(lo),
+                                               C.byref(up)))
+        return (px.value, lo.value, up.value) if want_bounds else px.value
+
+    def branching_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, num_branches, exercise_times,
+                        seed: int = 0, path_offset: int = 0, injected_rp: Optional[np.ndarray] = None,
+                        want_bounds: bool = False):
+        ex = np.ascontiguousarray(exercise_times, dtype=np.int32)
+        inj = None
+        if injected_rp is not None:
+            inj = np.ascontiguousarray(injected_rp, dtype=np.int32)
+            assert inj.ndim == 3 and inj.shape[1] == ps.n_paths and inj.shape[2] == num_branches
+        px, lo, up = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self._L.mcp_branching_price(
+            self._h, ps._h if ps is not None else None, r, strike, maturity, dt, int(bool(is_call)), num_branches,
+            ex.ctypes.data_as(C.POINTER(C.c_int)) if ex.size else None, int(ex.size), seed, path_offset,
+            inj.ctypes.data_as(capi._ip) if inj is not None else None, C.byref(px), C.byref(lo), C.byref(up)))
+        return (px.value, lo.value, up.value) if want_bounds else px.value
+
+    # -- exact-signature generator (host estimators + device generation) --------------------------
+    @staticmethod
+    def estimate_rbergomi_params(hist) -> dict:
+        L = capi.lib()
+        h = np.ascontiguousarray(hist, dtype=np.float64)
+        out = RbergomiParams()
+        rc = L.mcp_estimate_rbergomi_params(h.ctypes.data_as(capi._dp), h.size, C.byref(out))
+        if rc != 0:
+            raise McpError(rc, L.mcp_last_error(None).decode())
+        return {k: getattr(out, k) for k in ("S0", "r", "xi", "H", "eta", "rho", "dt")}
+
+    def generate_stock_price_paths(self, hist, forward_steps: int, path_num: int, seed: int = 0,
+                                   path_offset: int = 0) -> np.ndarray:
+        h = np.ascontiguousarray(hist, dtype=np.float64)
+        out = np.zeros((max(path_num, 0), max(forward_steps, 0) + 1), dtype=np.float64)
+        rows = (capi._dp * max(path_num, 1))(*[out[i].ctypes.data_as(capi._dp) for i in range(max(path_num, 0))])
+        self._chk(self._L.mcp_generate_stock_price_paths(self._h, h.ctypes.data_as(capi._dp), h.size, forward_steps,
+                                                         path_num, seed, path_offset, rows))
+        return out
+
     def price_rbergomi_lsm(self, model: dict, lsm: dict, n_paths: int, n_steps: int, seed: int = 0,
                            path_offset: int = 0):
         """Generate (native Philox) + LSM on the device: parameters in, a result out."""

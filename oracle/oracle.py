@@ -67,6 +67,11 @@ class _Port:
         L.orc_lsm_timemajor_f32.argtypes = [_fp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double,
                                             C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _ip, _dp, _dp, _lp]
         L.orc_lsm_timemajor_f32.restype = C.c_int
+        common = [_dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_asymptotic.argtypes = common + [C.c_double, C.c_double, _dp]
+        L.orc_martingale.argtypes = common + [C.c_int, C.c_int, _dp, _dp, _dp]
+        L.orc_branching.argtypes = common + [C.c_int, _ip, C.c_int, _ip, _dp, _dp, _dp]
+        L.orc_estimate_params.argtypes = [_dp, C.c_long, _dp]
         self.L = L
 
     def philox(self, ctr, key):
@@ -140,6 +145,45 @@ class _Port:
         return dict(price=price.value, stderr=se.value, coeffs=coeffs, first_ex=first, ex_mask=mask, V0=V0,
                     min_gap=gap.value, n_itm=nitm)
 
+    def asymptotic(self, paths, r, K, T, dt, is_call, sigma, dividend):
+        paths = _f64(paths)
+        px = C.c_double()
+        rc = self.L.orc_asymptotic(_ptr(paths, _dp), paths.shape[0], paths.shape[1], r, K, T, dt, int(is_call), sigma,
+                                   dividend, C.byref(px))
+        if rc != 0:
+            raise RuntimeError(f"orc_asymptotic rc={rc}")
+        return px.value
+
+    def martingale(self, paths, r, K, T, dt, is_call, p, max_iter=5):
+        paths = _f64(paths)
+        px, lo, up = C.c_double(), C.c_double(), C.c_double()
+        rc = self.L.orc_martingale(_ptr(paths, _dp), paths.shape[0], paths.shape[1], r, K, T, dt, int(is_call), p,
+                                   max_iter, C.byref(px), C.byref(lo), C.byref(up))
+        if rc != 0:
+            raise RuntimeError(f"orc_martingale rc={rc}")
+        return dict(price=px.value, primal=lo.value, dual=up.value)
+
+    def branching(self, paths, r, K, T, dt, is_call, num_branches, exercise_times, rp):
+        """rp: int32 [n_visited_dates][N][num_branches] resampled path indices (injected)."""
+        paths = _f64(paths)
+        ex = np.ascontiguousarray(exercise_times, dtype=np.int32)
+        q = np.ascontiguousarray(rp, dtype=np.int32)
+        px, lo, up = C.c_double(), C.c_double(), C.c_double()
+        rc = self.L.orc_branching(_ptr(paths, _dp), paths.shape[0], paths.shape[1], r, K, T, dt, int(is_call),
+                                  num_branches, _ptr(ex, _ip), ex.size, _ptr(q, _ip), C.byref(px), C.byref(lo),
+                                  C.byref(up))
+        if rc != 0:
+            raise RuntimeError(f"orc_branching rc={rc}")
+        return dict(price=px.value, lower=lo.value, upper=up.value)
+
+    def estimate_params(self, hist):
+        hist = _f64(hist)
+        out = np.zeros(7)
+        rc = self.L.orc_estimate_params(_ptr(hist, _dp), hist.size, _ptr(out, _dp))
+        if rc != 0:
+            raise RuntimeError(f"orc_estimate_params rc={rc}")
+        return dict(zip(("S0", "r", "xi", "H", "eta", "rho", "dt"), out))
+
     def lsm_timemajor_f32(self, slab, r, K, T, dt, is_call, p):
         """slab [M][N] float32 (the GPU's own layout).  Prices exactly those values widened to double."""
         slab = np.ascontiguousarray(slab, dtype=np.float32)
@@ -175,7 +219,7 @@ class _Ref:
         common = [_dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         L.ref_lsm_price.argtypes = common + [C.c_int, _dp]
         L.ref_martingale_price.argtypes = common + [C.c_int, C.c_int, _dp]
-        L.ref_branching_price.argtypes = common + [C.c_int, _ip, C.c_int, _dp]
+        L.ref_branching_price.argtypes = common + [C.c_int, _ip, C.c_int, _ip, C.c_long, C.POINTER(C.c_long), _dp]
         L.ref_asymptotic_price.argtypes = common + [C.c_double, C.c_double, _dp]
         L.ref_bench_rows.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.c_int, _dp, _dp, _dp, _dp]
@@ -234,13 +278,16 @@ class _Ref:
                                               int(is_call), p, max_iter, C.byref(px)))
         return px.value
 
-    def branching_price(self, paths, r, K, T, dt, is_call, num_branches, exercise_times):
+    def branching_price(self, paths, r, K, T, dt, is_call, num_branches, exercise_times, rp=None, want_used=False):
+        """rp: injected resampling indices in the reference's consumption order [path][date with continuation][branch]."""
         paths = _f64(paths)
         ex = np.ascontiguousarray(exercise_times, dtype=np.int32)
-        px = C.c_double()
+        px, used = C.c_double(), C.c_long(0)
+        q = np.ascontiguousarray(rp, dtype=np.int32).ravel() if rp is not None else None
         self._chk(self.L.ref_branching_price(_ptr(paths, _dp), paths.shape[0], paths.shape[1], r, K, T, dt,
-                                             int(is_call), num_branches, _ptr(ex, _ip), ex.size, C.byref(px)))
-        return px.value
+                                             int(is_call), num_branches, _ptr(ex, _ip), ex.size, _ptr(q, _ip),
+                                             q.size if q is not None else 0, C.byref(used), C.byref(px)))
+        return (px.value, used.value) if want_used else px.value
 
     def asymptotic_price(self, paths, r, K, T, dt, is_call, sigma, dividend):
         paths = _f64(paths)

@@ -340,3 +340,247 @@ int orc_lsm_timemajor_f32(const float *slab, long N, long M, double r, double K,
     free(pm);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The other three pricers and the generator's parameter estimators, restated.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* AsymptoticAnalysisPricer.cpp:8-36 -- closed-form early-exercise boundary */
+static double asym_boundary(int is_call, double t, double T, double K, double r, double D, double sigma)
+{
+    double eps = T - t, c0, b;
+    if (eps < 1e-10) return K;                          /* :10-11, :25-26 */
+    c0 = 0.5 * sigma * sqrt(eps * log(1.0 / eps));      /* :13, :28 (NaN when eps > 1) */
+    if (is_call) { b = K - c0; if (eps < 0.01) b += 0.5 * (D - r) * eps; }   /* :29-34 */
+    else         { b = K + c0; if (eps < 0.01) b -= 0.5 * (r - D) * eps; }   /* :14-19 */
+    return b;
+}
+
+/* AsymptoticAnalysisPricer.cpp:38-113.  Returns 0.0 on empty input (:48-50); sigma <= 0 is the caller's
+ * std::runtime_error (:51-53) -> rc -3 here. */
+int orc_asymptotic(const double *paths, long N, long M, double r, double K, double T, double dt, int is_call,
+                   double sigma, double dividend, double *price)
+{
+    long i, j, valid = 0;
+    double sum = 0.0;
+    *price = 0.0;
+    if (N <= 0 || M <= 0) return 0;
+    if (!(sigma > 0.0)) return -3;
+    for (i = 0; i < N; ++i) {
+        double best = 0.0;
+        for (j = 0; j < M; ++j) {                       /* :69-96 */
+            double t = (double)j * dt, S, b, pay, d;
+            int in;
+            if (t > T) break;                           /* :71 */
+            S = paths[i * M + j];
+            if (isnan(S) || isinf(S)) continue;         /* :74 */
+            b = asym_boundary(is_call, t, T, K, r, dividend, sigma);
+            in = is_call ? (S > b) : (S < b);           /* :80-85 */
+            if (!in) continue;
+            pay = payoff_fn(is_call, S, K);
+            if (isnan(pay) || isinf(pay)) continue;     /* :89 */
+            d = exp(-r * t) * pay;                      /* :90 */
+            if (d > best) best = d;
+        }
+        if (!isnan(best) && !isinf(best)) { sum += best; ++valid; }   /* :101-106 */
+    }
+    *price = valid > 0 ? sum / (double)valid : 0.0;     /* :108 */
+    return 0;
+}
+
+static double mart_df(long j, double dt, double T, double r) /* MartingaleOptimizationPricer.h:44-49 */
+{
+    double t = (double)j * dt;
+    if (t > T) t = T;
+    return exp(-r * t);
+}
+
+static double mart_eval(const double *c, int p, double S) /* MartingaleOptimizationPricer.cpp:180-188 */
+{
+    double v = 0.0, pw = 1.0;
+    int k;
+    for (k = 0; k <= p; ++k) { v += c[k] * pw; pw *= S; }
+    return v;
+}
+
+/* MartingaleOptimizationPricer.cpp:21-178, iteration by iteration exactly as written (primal, dual with the
+ * previous martingale, refit).  primal/dual (nullable) receive the last iteration's bounds. */
+int orc_martingale(const double *paths, long N, long M, double r, double K, double T, double dt, int is_call, int p,
+                   int max_iter, double *price, double *primal_out, double *dual_out)
+{
+    double c[ORC_LSQ_MAXN] = {0}, offset = 0.0, lower = 0.0, upper = 0.0;
+    long *stop, i, j;
+    double *A, *b;
+    int it, q;
+    if (N <= 0 || M <= 0) return -1;                    /* :31-33 */
+    if (max_iter <= 0) return -3;                       /* :34-36 */
+    if (p < 0 || p + 1 > ORC_LSQ_MAXN) return -1;
+    stop = (long *)malloc(sizeof(long) * (size_t)N);
+    A = (double *)malloc(sizeof(double) * (size_t)(2 * N) * (size_t)(p + 1));
+    b = (double *)malloc(sizeof(double) * (size_t)(2 * N));
+    if (!stop || !A || !b) return -2;
+    for (it = 1; it <= max_iter; ++it) {                /* :56-61 */
+        double sp = 0.0, sd = 0.0, s0 = 0.0;
+        for (i = 0; i < N; ++i) {                       /* :72-94 */
+            double best = 0.0;
+            long bi = 0;
+            for (j = 0; j < M; ++j) {
+                double dp;
+                if ((double)j * dt > T) break;
+                dp = payoff_fn(is_call, paths[i * M + j], K) * mart_df(j, dt, T, r);
+                if (dp > best) { best = dp; bi = j; }
+            }
+            stop[i] = bi;
+            sp += best;
+        }
+        for (i = 0; i < N; ++i) {                       /* :96-117 */
+            double best = 0.0;
+            for (j = 0; j < M; ++j) {
+                double S, cand;
+                if ((double)j * dt > T) break;
+                S = paths[i * M + j];
+                cand = payoff_fn(is_call, S, K) * mart_df(j, dt, T, r) - (mart_eval(c, p, S) - offset);
+                if (cand > best) best = cand;
+            }
+            sd += best;
+        }
+        lower = sp / (double)N;
+        upper = sd / (double)N;
+        if (2 * N >= p + 1) {                           /* :122-178 UpdateMartingale */
+            for (i = 0; i < N; ++i) {
+                long js = stop[i], jo = (js + M / 2) % M;
+                double Ss = paths[i * M + js], So = paths[i * M + jo], pw;
+                b[2 * i] = 0.5 * (payoff_fn(is_call, Ss, K) * mart_df(js, dt, T, r));
+                b[2 * i + 1] = 0.2 * (payoff_fn(is_call, So, K) * mart_df(jo, dt, T, r));
+                for (pw = 1.0, q = 0; q <= p; ++q) { A[(2 * i) * (p + 1) + q] = pw; pw *= Ss; }
+                for (pw = 1.0, q = 0; q <= p; ++q) { A[(2 * i + 1) * (p + 1) + q] = pw; pw *= So; }
+            }
+            orc_lstsq_minnorm(A, 2 * N, p + 1, b, c, NULL);   /* :166 */
+            for (i = 0; i < N; ++i) s0 += mart_eval(c, p, paths[i * M]);
+            offset = s0 / (double)N;                    /* :172-177 */
+        }
+    }
+    *price = 0.5 * (lower + upper);                     /* :63 */
+    if (primal_out) *primal_out = lower;
+    if (dual_out) *dual_out = upper;
+    free(stop); free(A); free(b);
+    return 0;
+}
+
+/* BranchingProcessPricer.cpp:13-134 with the resampled path indices INJECTED (the reference draws them from a
+ * std::mt19937 seeded by std::random_device, :84-86, shared between OpenMP threads).
+ *   rp: [n_visit][N][num_branches], n_visit = exercise dates visited before the first t > maturity.
+ * lower/upper nullable. */
+int orc_branching(const double *paths, long N, long M, double r, double K, double T, double dt, int is_call,
+                  int num_branches, const int *ex, int n_ex, const int32_t *rp, double *price, double *lower_out,
+                  double *upper_out)
+{
+    long i;
+    double sl = 0.0, su = 0.0;
+    int e, b;
+    if (N <= 0 || M <= 0) return -1;                    /* :22-24 */
+    if (n_ex <= 0) return -3;                           /* :25-27 */
+    if (!(K > 0.0)) return -4;                          /* :28-30 */
+    for (i = 0; i < N; ++i) {                           /* lower bound :41-71 */
+        double best = 0.0;
+        for (e = 0; e < n_ex; ++e) {
+            double t = (double)ex[e] * dt, d;
+            if (t > T) break;
+            d = exp(-r * t) * payoff_fn(is_call, paths[i * M + ex[e]], K);
+            if (d > best) { best = d; break; }
+        }
+        sl += best;
+    }
+    for (i = 0; i < N; ++i) {                           /* upper bound :73-134 */
+        double best = 0.0;
+        for (e = 0; e < n_ex; ++e) {
+            double t = (double)ex[e] * dt, now, cont = 0.0, better;
+            if (t > T) break;
+            now = exp(-r * t) * payoff_fn(is_call, paths[i * M + ex[e]], K);
+            if (ex[e] < ex[n_ex - 1]) {                 /* :103 */
+                double sf = 0.0;
+                for (b = 0; b < num_branches; ++b) {
+                    long q = rp[((long)e * N + i) * num_branches + b], k;
+                    double bf = 0.0;
+                    for (k = ex[e] + 1; k < M; ++k) {   /* :110-121 */
+                        double tk = (double)k * dt, d;
+                        if (tk > T) break;
+                        d = exp(-r * (tk - t)) * payoff_fn(is_call, paths[q * M + k], K);
+                        if (d > bf) bf = d;
+                    }
+                    sf += bf;
+                }
+                cont = (sf / (double)num_branches) * exp(-r * t);   /* :123 */
+            }
+            better = now < cont ? cont : now;           /* :126 */
+            if (better > best) best = better;
+        }
+        su += best;
+    }
+    if (lower_out) *lower_out = sl / (double)N;
+    if (upper_out) *upper_out = su / (double)N;
+    *price = 0.5 * (sl / (double)N + su / (double)N);   /* :38 */
+    return 0;
+}
+
+/* RoughVolatility.cpp:20-42 */
+static double est_mean(const double *v, long n) { double s = 0.0; long i; for (i = 0; i < n; ++i) s += v[i]; return n ? s / (double)n : 0.0; }
+static double est_var(const double *v, long n)
+{
+    double m, a = 0.0; long i;
+    if (n < 2) return 0.0;
+    m = est_mean(v, n);
+    for (i = 0; i < n; ++i) a += (v[i] - m) * (v[i] - m);
+    return a / (double)(n - 1);
+}
+
+/* RoughVolatility.cpp:72-169, :324-331 -> out7 = S0, r, xi, H, eta, rho, dt */
+int orc_estimate_params(const double *hist, long n_hist, double *out7)
+{
+    long n = n_hist - 1, i, w, nw = 0;
+    double *ret, *sq, *prof, *seg, lw[64], lf[64], var, m, mx, my, cov = 0.0, rho, H = 0.5;
+    if (n_hist < 2) return -3;                          /* :317-319 */
+    ret = (double *)malloc(sizeof(double) * (size_t)n * 4);
+    if (!ret) return -2;
+    sq = ret + n; prof = sq + n; seg = prof + n;
+    for (i = 0; i < n; ++i) { ret[i] = log(hist[i + 1] / hist[i]); sq[i] = ret[i] * ret[i]; }   /* :126-133 */
+    var = est_var(ret, n);
+    mx = est_mean(ret, n); my = est_mean(sq, n);
+    if (n >= 2) { for (i = 0; i < n; ++i) cov += (ret[i] - mx) * (sq[i] - my); cov /= (double)(n - 1); } else cov = 0.0;
+    rho = cov / sqrt(var * est_var(sq, n));             /* :157-164 */
+    if (rho > 0.0) rho = -0.3;                          /* :165-167 */
+    if (n >= 2) {                                       /* DFA :72-122 */
+        m = est_mean(ret, n);
+        for (i = 0; i < n; ++i) prof[i] = ret[i] - m;
+        for (i = 1; i < n; ++i) prof[i] += prof[i - 1];
+        for (w = 4; w <= n / 4; w *= 2) {
+            long start, cnt = 0;
+            double fs = 0.0, tm = 0.0;
+            for (i = 0; i < w; ++i) tm += (double)(i + 1);
+            tm /= (double)w;
+            for (start = 0; start + w <= n; start += w) {
+                double ym = 0.0, num = 0.0, den = 0.0, ss = 0.0;
+                for (i = 0; i < w; ++i) { seg[i] = prof[start + i]; ym += seg[i]; }
+                ym /= (double)w;
+                for (i = 0; i < w; ++i) { num += ((double)(i + 1) - tm) * (seg[i] - ym); den += ((double)(i + 1) - tm) * ((double)(i + 1) - tm); }
+                if (!(fabs(den) < 1e-14)) {
+                    double sl = num / den, ic = ym - sl * tm;
+                    for (i = 0; i < w; ++i) seg[i] -= sl * (double)(i + 1) + ic;
+                }
+                for (i = 0; i < w; ++i) ss += seg[i] * seg[i];
+                fs += sqrt(ss / (double)w);
+                ++cnt;
+            }
+            if (cnt > 0 && fs / (double)cnt > 0.0 && nw < 64) { lw[nw] = log((double)w); lf[nw] = log(fs / (double)cnt); ++nw; }
+        }
+        if (nw >= 2) {
+            double sx = 0, sy = 0, sxx = 0, sxy = 0;
+            for (i = 0; i < nw; ++i) { sx += lw[i]; sy += lf[i]; sxx += lw[i] * lw[i]; sxy += lw[i] * lf[i]; }
+            H = ((double)nw * sxy - sx * sy) / ((double)nw * sxx - sx * sx);
+        }
+    }
+    out7[0] = hist[n_hist - 1]; out7[1] = 0.04; out7[2] = var / (1.0 / 252.0); out7[3] = H;
+    out7[4] = 2.0 * sqrt(var); out7[5] = rho; out7[6] = 1.0 / 252.0;
+    free(ret);
+    return 0;
+}

@@ -36,6 +36,10 @@ extern "C" {
 thread_local const double* orc_inject_ptr = nullptr;
 thread_local std::size_t orc_inject_left = 0;
 thread_local std::size_t orc_inject_used = 0;
+// resampling indices for BranchingProcessPricer.cpp (oracle/shim_uniform.h)
+thread_local const int* orc_index_ptr = nullptr;
+thread_local std::size_t orc_index_left = 0;
+thread_local std::size_t orc_index_used = 0;
 }
 
 namespace {
@@ -177,13 +181,20 @@ int ref_martingale_price(const double* paths, long N, long M, double r, double K
     });
 }
 
+// rp (nullable): resampled path indices in the reference's consumption order [path][date with continuation][branch]
+// (BranchingProcessPricer.cpp:93-110, serial build); n_rp entries; *used (nullable) receives how many were drawn.
 int ref_branching_price(const double* paths, long N, long M, double r, double K, double T, double dt, int isCall,
-                        int numBranches, const int* ex, int n_ex, double* price) {
+                        int numBranches, const int* ex, int n_ex, const int* rp, long n_rp, long* used, double* price) {
     return guarded([&] {
         auto vv = to_vv(paths, N, M);
         std::vector<int> e(ex, ex + n_ex);
         BranchingProcesses bp;
+        orc_index_ptr = rp;
+        orc_index_left = rp ? static_cast<std::size_t>(n_rp) : 0;
+        orc_index_used = 0;
+        struct Reset { ~Reset() { orc_index_ptr = nullptr; orc_index_left = 0; } } reset;
         *price = bp.PredictOptionPrice(vv, r, K, T, dt, isCall != 0, numBranches, e);
+        if (used) *used = static_cast<long>(orc_index_used);
     });
 }
 

@@ -74,3 +74,23 @@ def test_reference_plugin_error_message_without_device():
     import montecarlooptionspricer_b200 as m
     with pytest.raises(RuntimeError, match="LSM::PredictOptionPrice: Empty pricePaths."):
         m.LSM(engine=None).PredictOptionPrice([], 0.05, 100.0, 1.0, 0.02, False, 2)
+
+
+def test_cpp_plugin_library_builds_and_exports_the_reference_classes():
+    """libmcp_b200_plugins.so: the five reference class names with their method names (mangled) are exported."""
+    from montecarlooptionspricer_b200 import build
+    build.build_all()
+    assert os.path.exists(build.PLUGINS) and os.path.exists(build.DEMO)
+    out = subprocess.run(["nm", "-DC", "--defined-only", build.PLUGINS], capture_output=True, text=True, check=True).stdout
+    for sym in ("mcp_b200::RoughVolatility::GenerateStockPricePaths(std::vector<double", "mcp_b200::LSM::PredictOptionPrice(",
+                "mcp_b200::MartingaleOptimization::PredictOptionPrice(", "mcp_b200::BranchingProcesses::PredictOptionPrice(",
+                "mcp_b200::AsymptoticAnalysis::PredictOptionPrice(", "mcp_b200::Engine::thread_default()"):
+        assert sym in out, sym
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_cpp_plugins_fail_loudly_without_a_device(tmp_path):
+    from montecarlooptionspricer_b200 import build
+    build.build_all()
+    res = subprocess.run([build.DEMO, str(tmp_path / "x.bin"), "1", "8", "30"], capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0 and "no CPU fallback" in res.stderr

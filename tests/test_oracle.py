@@ -182,3 +182,87 @@ def test_config1_known_answers(port):
     paths = port.gbm_paths(100, 0.05, 0.2, 0.02, 50, rng.standard_normal((100_000, 50)))
     o = port.lsm(paths, CFG1["r"], CFG1["K"], CFG1["T"], 0.02, False, 3)
     assert bs < o["price"] and berm - 3 * o["stderr"] < o["price"] < berm * 1.02
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other three pricers and the generator's estimators -- port vs the compiled reference
+# ------------------------------------------------------------------------------------------------------
+def _golden_paths():
+    g = np.load(os.path.join(G, "pricers_ref.npz"))
+    return g, g["paths_f32"].astype(np.float64)
+
+
+def test_port_asymptotic_and_martingale_vs_golden(port):
+    g, P = _golden_paths()
+    assert port.asymptotic(P, 0.05, 100.0, 1.0, 0.02, False, 0.2, 0.0) == pytest.approx(float(g["asym_put"]), rel=1e-13)
+    assert port.asymptotic(P, 0.05, 100.0, 1.0, 0.02, True, 0.2, 0.01) == pytest.approx(float(g["asym_call"]), rel=1e-13)
+    assert port.martingale(P, 0.05, 100.0, 1.0, 0.02, False, 2, 5)["price"] == pytest.approx(float(g["mart_put_p2"]), rel=1e-10)
+    assert port.martingale(P, 0.05, 100.0, 1.0, 0.02, True, 2, 5)["price"] == pytest.approx(float(g["mart_call_p2"]), rel=1e-10)
+
+
+@pytest.mark.parametrize("is_call,K,T,p,iters", [(False, 100.0, 1.0, 2, 5), (True, 95.0, 1.0, 3, 2), (False, 105.0, 0.5, 1, 1),
+                                                (False, 100.0, 1.0, 2, 3)])
+def test_port_pricers_match_reference(ref, port, is_call, K, T, p, iters):
+    _, P = _golden_paths()
+    P = P[:1500]
+    assert port.asymptotic(P, 0.05, K, T, 0.02, is_call, 0.25, 0.01) == pytest.approx(
+        ref.asymptotic_price(P, 0.05, K, T, 0.02, is_call, 0.25, 0.01), rel=1e-13, abs=1e-15)
+    assert port.martingale(P, 0.05, K, T, 0.02, is_call, p, iters)["price"] == pytest.approx(
+        ref.martingale_price(P, 0.05, K, T, 0.02, is_call, p, iters), rel=1e-9)
+
+
+def test_martingale_fit_does_not_depend_on_the_iteration_count(ref):
+    """Stopping indices and regression samples depend only on the paths (MartingaleOptimizationPricer.cpp:72-94,
+    :130-150), so every maxIterations >= 2 returns the same value -- the fact the two-pass device kernel relies on."""
+    _, P = _golden_paths()
+    v = [ref.martingale_price(P[:800], 0.05, 100.0, 1.0, 0.02, False, 2, k) for k in (1, 2, 3, 5)]
+    assert v[1] == v[2] == v[3] and v[0] != v[1]
+
+
+def test_port_branching_matches_reference_with_injected_indices(ref, port):
+    """The reference's Branching TU compiled serially with oracle/shim_uniform.h consumes the injected path indices in
+    the order [path][date with continuation][branch]; the port takes them as [date][path][branch]."""
+    _, P = _golden_paths()
+    N, B = 300, 10
+    rng = np.random.default_rng(3)
+    for ex, T in ((np.arange(0, 50), 1.0), (np.arange(0, 50, 3), 0.61), (np.array([5, 6, 40]), 1.0)):
+        n_visit = int(np.sum(ex * 0.02 <= T))
+        rp = rng.integers(0, N, size=(n_visit, N, B)).astype(np.int32)
+        got = port.branching(P[:N], 0.05, 100.0, T, 0.02, False, B, ex, rp)
+        n_cont = int(np.sum(ex[:n_visit] < ex[-1]))
+        want, used = ref.branching_price(P[:N], 0.05, 100.0, T, 0.02, False, B, ex,
+                                         rp=np.ascontiguousarray(rp[:n_cont].transpose(1, 0, 2)), want_used=True)
+        assert used == N * n_cont * B
+        assert got["price"] == pytest.approx(want, rel=1e-12)
+        assert got["lower"] <= got["upper"]
+
+
+def test_port_estimators_match_reference_and_golden(ref, port):
+    g = np.load(os.path.join(G, "generate_paths_ref.npz"))
+    est = port.estimate_params(g["hist"])
+    for k, v in zip(("xi", "H", "eta", "rho", "S0"), g["est"]):
+        assert est[k] == pytest.approx(float(v), rel=1e-12), k
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 17, 64, 500, 1826):
+        hist = 50.0 * np.exp(np.cumsum(0.02 * rng.standard_normal(n)))
+        a, b = port.estimate_params(hist), ref.estimate_params(hist)
+        for k in ("xi", "H", "eta", "rho", "S0"):
+            assert (np.isnan(a[k]) and np.isnan(b[k])) or a[k] == pytest.approx(b[k], rel=1e-11, abs=1e-300), (n, k)
+
+
+def test_product_estimators_on_the_host_match_the_oracle(port):
+    """mcp_estimate_rbergomi_params is pure host arithmetic (no device): check it here, on the CPU box."""
+    import montecarlooptionspricer_b200 as m
+    g = np.load(os.path.join(G, "generate_paths_ref.npz"))
+    got = m.Engine.estimate_rbergomi_params(g["hist"])
+    for k, v in zip(("xi", "H", "eta", "rho", "S0"), g["est"]):
+        assert got[k] == pytest.approx(float(v), rel=1e-12), k
+    assert got["r"] == 0.04 and got["dt"] == 1.0 / 252.0
+    rng = np.random.default_rng(6)
+    for n in (2, 5, 40, 700):
+        hist = 80.0 * np.exp(np.cumsum(0.015 * rng.standard_normal(n)))
+        a, b = m.Engine.estimate_rbergomi_params(hist), port.estimate_params(hist)
+        for k in b:
+            assert (np.isnan(a[k]) and np.isnan(b[k])) or a[k] == pytest.approx(b[k], rel=1e-11, abs=1e-300), (n, k)
+    with pytest.raises(m.McpError, match="Historical prices vector too small."):
+        m.Engine.estimate_rbergomi_params([100.0])
