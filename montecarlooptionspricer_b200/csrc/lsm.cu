@@ -28,6 +28,7 @@
 // eigen-decomposition with a relative cut, the normal-equation image of Eigen's singular-value threshold.
 // All decisions are taken in fp64 on the stored path values, exactly like the reference.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -68,6 +69,8 @@ struct SweepArgs {
     int do_moments;  // accumulate moments of step j-1
     int do_final;    // j == 0: accumulate sum V0
     int solve_here;  // single GPU: the last CTA to finish also solves step j-1 (no extra launches)
+    int64_t pin_paths;  // leading paths whose carry lines are kept L2-resident across sweeps
+    int pin_mode;       // 1: evict_last hints, 2: plain accesses under a persisting access-policy window
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
@@ -305,6 +308,187 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast_kernel(SweepArgs a) 
     if (a.do_moments || a.do_final) sweep_epilogue<NV, P>(a, acc);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// sweep(j), THROUGHPUT kernel v2: same arithmetic as lsm_sweep_fast_kernel, restructured for Blackwell.
+//   * packed fp32x2 math (FFMA2 / FADD2 / FMUL2, one issue slot per two paths): the v1 kernel issued ~77
+//     instructions per path and ran at 63% issue utilisation with DRAM only 56% busy -- it was as much
+//     instruction-bound as bandwidth-bound;
+//   * the in-the-money filter of the moments is a 0/1 multiplier on (x, y) instead of a divergent branch
+//     (x = 0 kills every power, y = 0 every cross moment);
+//   * the fp64 side of the accumulation lives in shared memory ([NV][256] doubles), not in 2 NV registers;
+//   * carry lines of the first `pin_paths` paths are accessed with an L2 evict_last policy so that they stay
+//     resident in the 126 MB L2 across all sweeps (each such line saves one HBM read AND one write-back per
+//     step); everything that is touched once per sweep is streamed (evict_first).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+// 256-bit global accesses with an L2 eviction priority (sm_100a: LDG/STG.E.256 with .EFL2 / .ENL2 / .ELL2).
+struct F8 {
+    float2 q[4];
+};
+#define MCP_LD8(NAME, MOD)                                                                                                     \
+    __device__ __forceinline__ F8 NAME(const float* p) {                                                                       \
+        uint32_t r[8];                                                                                                         \
+        asm volatile("ld.global" MOD ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                \
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])          \
+                     : "l"(p));                                                                                                \
+        F8 o;                                                                                                                  \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) o.q[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])); \
+        return o;                                                                                                              \
+    }
+#define MCP_ST8(NAME, MOD)                                                                                                     \
+    __device__ __forceinline__ void NAME(float* p, const F8& o) {                                                              \
+        asm volatile("st.global" MOD ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(o.q[0].x)),      \
+                     "r"(__float_as_uint(o.q[0].y)), "r"(__float_as_uint(o.q[1].x)), "r"(__float_as_uint(o.q[1].y)),           \
+                     "r"(__float_as_uint(o.q[2].x)), "r"(__float_as_uint(o.q[2].y)), "r"(__float_as_uint(o.q[3].x)),           \
+                     "r"(__float_as_uint(o.q[3].y))                                                                            \
+                     : "memory");                                                                                              \
+    }
+MCP_LD8(ld8_stream, ".L1::no_allocate.L2::evict_first")  // touched once per sweep
+MCP_LD8(ld8_keep, ".L1::no_allocate.L2::evict_normal")   // S_{j-1}: read again by the next sweep
+MCP_LD8(ld8_pinned, ".L1::no_allocate.L2::evict_last")   // carry lines meant to stay L2-resident across sweeps
+MCP_ST8(st8_stream, ".L2::evict_first")
+MCP_ST8(st8_pinned, ".L2::evict_last")
+MCP_ST8(st8_keep, ".L2::evict_normal")
+
+template <int P>
+struct FastConsts {
+    float2 c[P + 1];
+    float2 nmu, is, nmu_p, is_p;  // -mu, 1/s of step j and of step j-1
+    float2 sg, nsK, nsKlo;        // payoff = max(sg*S + nsK + nsKlo, 0)
+    float2 d_hi, d_lo;            // e^{-r dt} as a two-float product
+};
+
+// One group of 8 consecutive paths.  TAIL: the (single) ragged last group, lanes >= nvalid are masked out.
+template <int P, bool TAU, bool TAIL>
+__device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts<P>& k, const float* __restrict__ Sj, const float* __restrict__ Sp,
+                                            float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+    const bool pinned = i0 < a.pin_paths;
+    const F8 s8 = ld8_stream(Sj + i0);
+    F8 p8 = s8, v8 = s8;
+    if (a.do_moments) p8 = ld8_keep(Sp + i0);
+    if (mode != 2) v8 = pinned ? (a.pin_mode == 2 ? ld8_keep(V + i0) : ld8_pinned(V + i0)) : ld8_stream(V + i0);
+    const float2(&s)[4] = s8.q;
+    const float2(&sp)[4] = p8.q;
+    float2(&v)[4] = v8.q;
+    const int nvalid = TAIL ? (int)(a.n - i0) : 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 pay = __fadd2_rn(__ffma2_rn(s[q], k.sg, k.nsK), k.nsKlo);  // include/core/common.h:8-14
+        pay.x = fmaxf(pay.x, 0.f);
+        pay.y = fmaxf(pay.y, 0.f);
+        if (mode == 2) {
+            v[q] = pay;  // LSMPricer.cpp:37-40
+        } else {
+            const float2 vd = __ffma2_rn(v[q], k.d_lo, __fmul2_rn(v[q], k.d_hi));
+            if (mode == 1) {
+                v[q] = vd;  // LSMPricer.cpp:43-49
+            } else {
+                const float2 x = __fmul2_rn(__fadd2_rn(s[q], k.nmu), k.is);
+                float2 cont = k.c[P];
+#pragma unroll
+                for (int m = P - 1; m >= 0; --m) cont = __ffma2_rn(cont, x, k.c[m]);
+                // ITM: V = max(payoff, fitted)  (:78-86);  payoff < 1e-14: discounted carry (:89-94);  == 1e-14: 0 (:35)
+                v[q].x = pay.x > 1e-14f ? fmaxf(pay.x, cont.x) : (pay.x < 1e-14f ? vd.x : 0.f);
+                v[q].y = pay.y > 1e-14f ? fmaxf(pay.y, cont.y) : (pay.y < 1e-14f ? vd.y : 0.f);
+                if (TAU) {
+                    if (pay.x > 1e-14f && !(pay.x < cont.x) && 2 * q < nvalid) a.tau[i0 + 2 * q] = a.j;
+                    if (pay.y > 1e-14f && !(pay.y < cont.y) && 2 * q + 1 < nvalid) a.tau[i0 + 2 * q + 1] = a.j;
+                }
+            }
+        }
+    }
+    if (pinned) { if (a.pin_mode == 2) st8_keep(V + i0, v8); else st8_pinned(V + i0, v8); }
+    else st8_stream(V + i0, v8);
+    if (a.do_moments) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 pp = __fadd2_rn(__ffma2_rn(sp[q], k.sg, k.nsK), k.nsKlo);  // payoff of step j-1 (sign test only)
+            float2 m = make_float2(pp.x > 1e-14f ? 1.f : 0.f, pp.y > 1e-14f ? 1.f : 0.f);  // LSMPricer.cpp:51-58
+            if (TAIL) {
+                if (2 * q >= nvalid) m.x = 0.f;
+                if (2 * q + 1 >= nvalid) m.y = 0.f;
+            }
+            const float2 x = __fmul2_rn(__fmul2_rn(__fadd2_rn(sp[q], k.nmu_p), k.is_p), m);
+            const float2 y = __fmul2_rn(__ffma2_rn(v[q], k.d_lo, __fmul2_rn(v[q], k.d_hi)), m);  // LSMPricer.cpp:69
+            la[0] = __fadd2_rn(la[0], m);
+            la[2 * P + 1] = __fadd2_rn(la[2 * P + 1], y);
+            float2 xp = x;
+#pragma unroll
+            for (int e = 1; e <= 2 * P; ++e) {
+                la[e] = __fadd2_rn(la[e], xp);
+                if (e <= P) la[2 * P + 1 + e] = __ffma2_rn(xp, y, la[2 * P + 1 + e]);
+                if (e < 2 * P) xp = __fmul2_rn(xp, x);
+            }
+        }
+    }
+    if (a.do_final) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 w = v[q];
+            if (TAIL) {
+                if (2 * q >= nvalid) w.x = 0.f;
+                if (2 * q + 1 >= nvalid) w.y = 0.f;
+            }
+            la[0] = __fadd2_rn(la[0], w);
+        }
+    }
+}
+
+template <int P, bool TAU, int OCC>
+__global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs a) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    constexpr int FLUSH = 8;  // groups (x8 paths) between fp32 -> fp64 folds
+    __shared__ double sacc[NV][LSM_NT];
+    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    float* __restrict__ V = reinterpret_cast<float*>(a.V);
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+
+    FastConsts<P> k;
+#pragma unroll
+    for (int m = 0; m <= P; ++m) k.c[m] = splat2((float)a.d.coef[(int64_t)a.j * COEF_LD + m]);
+    k.nmu = splat2(-(float)a.d.mu[a.j]);
+    k.is = splat2((float)a.d.inv_s[a.j]);
+    k.nmu_p = splat2(-(float)a.d.mu[a.j > 0 ? a.j - 1 : 0]);
+    k.is_p = splat2((float)a.d.inv_s[a.j > 0 ? a.j - 1 : 0]);
+    const float sgn = a.is_call ? 1.f : -1.f;
+    const float K_hi = (float)a.K, K_lo = (float)(a.K - (double)K_hi);
+    k.sg = splat2(sgn);
+    k.nsK = splat2(-sgn * K_hi);
+    k.nsKlo = splat2(-sgn * K_lo);
+    const float d_hi = (float)a.disc;
+    k.d_hi = splat2(d_hi);
+    k.d_lo = splat2((float)(a.disc - (double)d_hi));
+
+    float2 la[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m][threadIdx.x] = 0.0; }
+    int since = 0;
+
+    const int64_t ngroup = (a.n + 7) >> 3, nfull = a.n >> 3, gstride = (int64_t)gridDim.x * LSM_NT;
+    for (int64_t ig = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; ig < ngroup; ig += gstride) {
+        const int64_t g = (a.j & 1) ? (ngroup - 1 - ig) : ig;  // serpentine: what the previous sweep touched last is read first
+        if (g < nfull) fast2_group<P, TAU, false>(a, k, Sj, Sp, V, g * 8, mode, la);
+        else fast2_group<P, TAU, true>(a, k, Sj, Sp, V, g * 8, mode, la);
+        if (++since == FLUSH) {
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                sacc[m][threadIdx.x] += (double)la[m].x + (double)la[m].y;
+                la[m] = make_float2(0.f, 0.f);
+            }
+            since = 0;
+        }
+    }
+    if (a.do_moments || a.do_final) {
+        double acc[NV];
+#pragma unroll
+        for (int m = 0; m < NV; ++m) acc[m] = sacc[m][threadIdx.x] + ((double)la[m].x + (double)la[m].y);
+        sweep_epilogue<NV, P>(a, acc);
+    }
+}
+
 // Sum the per-CTA partial rows in a fixed order -> out[0..nv).
 __global__ void __launch_bounds__(256) lsm_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
     __shared__ double red[8][32];
@@ -454,7 +638,27 @@ SweepFn pick_sweep_fast(int p) {
     }
 }
 
-SweepFn pick_sweep(int slab_dtype, int carry_dtype, int p) {
+template <bool TAU, int OCC>
+SweepFn pick_sweep_fast2(int p) {
+    switch (p) {
+        case 0: return lsm_sweep_fast2_kernel<0, TAU, OCC>;
+        case 1: return lsm_sweep_fast2_kernel<1, TAU, OCC>;
+        case 2: return lsm_sweep_fast2_kernel<2, TAU, OCC>;
+        case 3: return lsm_sweep_fast2_kernel<3, TAU, OCC>;
+        case 4: return lsm_sweep_fast2_kernel<4, TAU, OCC>;
+        case 5: return lsm_sweep_fast2_kernel<5, TAU, OCC>;
+        default: return lsm_sweep_fast2_kernel<6, TAU, OCC>;
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+SweepFn pick_sweep(int slab_dtype, int carry_dtype, int p, bool want_tau) {
+    if (slab_dtype == MCP_F32 && carry_dtype == MCP_F32 && env_int("MCP_SWEEP_IMPL", 2) == 2)
+        return want_tau ? pick_sweep_fast2<true, 3>(p) : (env_int("MCP_SWEEP_OCC", 3) == 4 ? pick_sweep_fast2<false, 4>(p) : pick_sweep_fast2<false, 3>(p));
     if (slab_dtype == MCP_F32) return carry_dtype == MCP_F32 ? pick_sweep_fast(p) : pick_sweep<float, double>(p);
     return carry_dtype == MCP_F32 ? pick_sweep<double, float>(p) : pick_sweep<double, double>(p);
 }
@@ -510,7 +714,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     const size_t csz = prm->carry == MCP_F32 ? 4 : 8;
     const uint64_t launches0 = ctx->launches;
 
-    SweepFn sweep = pick_sweep(ps->dtype, prm->carry, p);
+    SweepFn sweep = pick_sweep(ps->dtype, prm->carry, p, first_exercise != nullptr);
     int occ = 0;
     MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep, LSM_NT, 0));
     if (occ < 1) occ = 1;
@@ -567,6 +771,31 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
     a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
     a.solve_here = (ctx->nranks <= 1 || !ctx->comm) ? 1 : 0;
+    a.pin_paths = ((int64_t)env_int("MCP_SWEEP_PIN_MB", 0) << 20) / 4 / 8 * 8;  // carry bytes kept L2-resident
+    a.pin_mode = env_int("MCP_SWEEP_PIN_MODE", 1);
+    if (a.pin_paths > N) a.pin_paths = N / 8 * 8;
+    bool window_set = false;
+    if (a.pin_paths > 0 && a.pin_mode == 2 && prm->carry == MCP_F32) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        size_t want = (size_t)a.pin_paths * 4;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        if (want > (size_t)max_window) want = (size_t)max_window;
+        a.pin_paths = (int64_t)(want / 4 / 8 * 8);
+        if (getenv("MCP_DEBUG")) fprintf(stderr, "[mcp] persisting L2: max %d B, window max %d B, using %zu B\n", max_persist, max_window, want);
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = dV;
+            attr.accessPolicyWindow.num_bytes = want;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        }
+        cudaGetLastError();
+    }
     const int nm = 3 * p + 2;
     for (int j = M - 1; j >= 0; --j) {
         a.j = j;
@@ -582,6 +811,12 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
             lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD);
             MCP_LAUNCH_CHECK(ctx);
         }
+    }
+    if (window_set) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
     }
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
