@@ -36,7 +36,7 @@ namespace {
 constexpr int NT = 512;  // threads per CTA: 16 warps share one 32-path tile; 2 CTAs/SM -> 32 resident warps
 
 struct RbParams {
-    float S0, xi, r_dt, half_dt, sq_dt, rho, rho_c;  // r*dt, 0.5*dt, sqrt(dt), rho, sqrt(1-rho^2)
+    float S0, rd2, nh2, lsq, rho, rho_c;  // r dt log2e, -dt/2 log2e, log2(sqrt(dt) log2e), rho, sqrt(1-rho^2)
     int n;        // steps
     int Mp;       // DFT length = nextPow2(n)
     int lgMp;     // log2(Mp)
@@ -58,18 +58,23 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return y;
 }
 
+struct RbParams;
+__device__ __forceinline__ float log2_increment(float e, float w, const RbParams& P);
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed fp32x2 instruction (Blackwell FADD2 / FFMA2): a float2 lives in an aligned
+// register pair, so the two halves of a butterfly cost one issue slot instead of two
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
 // forward (e^{-i theta}) 4-point DFT in place
 __device__ __forceinline__ void dft4(float2& c0, float2& c1, float2& c2, float2& c3) {
-    const float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), o0 = cadd(c1, c3), o1 = mul_mi(csub(c1, c3));
+    const float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), o0 = cadd(c1, c3), d = csub(c1, c3);
     c0 = cadd(e0, o0);
     c2 = csub(e0, o0);
-    c1 = cadd(e1, o1);
-    c3 = csub(e1, o1);
+    c1 = make_float2(e1.x + d.y, e1.y - d.x);  // e1 + (-i) d : the rotation swaps the halves, scalar adds
+    c3 = make_float2(e1.x - d.y, e1.y + d.x);  // e1 - (-i) d
 }
 
 // forward 8-point DFT: y[s] = sum_q x[q] w8^{qs}; result returned in natural order in x[]
@@ -125,6 +130,14 @@ __device__ __forceinline__ void dftR(float2 (&x)[R]) {
     }
 }
 
+// Log2-increment of one step from e = log2 v = X log2e + log2 xi - eta^2 t^{2H} log2e / 2 (tables carry the constants):
+//   v = 2^e,  sqrt(v) sqrt(dt) log2e = 2^{e/2 + lsq}  (v > 0 always, so the reference's max(0, v) is vacuous, :362),
+//   d = ((r - v/2) dt + sqrt(v) sqrt(dt) dW) log2e                                     RoughVolatility.cpp:356-363
+__device__ __forceinline__ float log2_increment(float e, float w, const RbParams& P) {
+    const float v = fast_ex2(e), sv = fast_ex2(fmaf(e, 0.5f, P.lsq));
+    return fmaf(sv, w, fmaf(v, P.nh2, P.rd2));
+}
+
 // One DIF pass of radix R = 2^LGR over sub-transforms of length L = 2^lgL, for the TP paths of the tile.
 //   inputs  x_q = A[base + q*L/R],  outputs  y_s * w_L^{j s}  back to A[base + s*L/R].  All index math is shifts.
 template <int LGR, int TP>
@@ -166,9 +179,8 @@ __device__ __forceinline__ void last_pass(const float2* __restrict__ A, float* _
         for (int s = 0; s < R; ++s) {
             const int m = rev[(bf << LGR) + s];
             if (m < P.n) {
-                const float v = P.xi * fast_ex2(x[out_slot<R>(s)].x + comp2[m]);
                 float* w = W + (size_t)m * TP + p;
-                *w = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * *w;
+                *w = log2_increment(x[out_slot<R>(s)].x + comp2[m], *w, P);
             }
         }
     }
@@ -301,36 +313,56 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
             }
             if (P.n_stage == 0) {  // n == 1: the transform is the identity
                 if (tid < TP) {
-                    const float v = P.xi * fast_ex2(A[p].x + comp2[0]);
-                    W[p] = fmaf(-P.half_dt, v, P.r_dt) + fast_sqrt(fmaxf(v, 0.f)) * P.sq_dt * W[p];
+                    W[p] = log2_increment(A[p].x + comp2[0], W[p], P);
                 }
                 __syncthreads();
             }
         }
 
-        // ---- phase 3: log-space prefix sum over time: chunk-local scan + cross-chunk offset ----------------
-        float run = 0.f;
-        if (has_chunk) {
-            float* w = W + (size_t)k0 * TP + p;
-            const int kend = min(k1, n);
-#pragma unroll 4
-            for (int k = k0; k < kend; ++k, w += TP) {
-                run += *w;
-                *w = run;
-            }
-        }
-        tot[g * TP + p] = run;
-        __syncthreads();
-        float off = 0.f;
-        for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
-        if (live) {
-            if (g == 0) out[path] = P.S0;
-            if (has_chunk) {
+        // ---- phase 3: log2-space prefix sum over time: chunk-local scan + cross-chunk offset, S = S0 2^(.) ----------
+        if (CH == 16 && G * 16 == Mp) {
+            // the common shape (252 steps: 16 warps x 16 steps): the chunk stays in registers between scan and store
+            float c[16];
+            const float* w = W + (size_t)k0 * TP + p;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) c[t] = w[(size_t)t * TP];  // rows >= n hold 0
+#pragma unroll
+            for (int t = 1; t < 16; ++t) c[t] += c[t - 1];
+            tot[g * TP + p] = c[15];
+            __syncthreads();
+            float off = 0.f;
+            for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
+            if (live) {
+                if (g == 0) out[path] = P.S0;
                 float* o = out + (int64_t)(k0 + 1) * P.ld + path;
-                const float* w = W + (size_t)k0 * TP + p;
+#pragma unroll
+                for (int t = 0; t < 16; ++t, o += P.ld)
+                    if (k0 + t < n) *o = P.S0 * fast_ex2(off + c[t]);
+            }
+        } else {
+            float run = 0.f;
+            if (has_chunk) {
+                float* w = W + (size_t)k0 * TP + p;
                 const int kend = min(k1, n);
 #pragma unroll 4
-                for (int k = k0; k < kend; ++k, o += P.ld, w += TP) *o = P.S0 * fast_ex2(1.4426950408889634f * (off + *w));
+                for (int k = k0; k < kend; ++k, w += TP) {
+                    run += *w;
+                    *w = run;
+                }
+            }
+            tot[g * TP + p] = run;
+            __syncthreads();
+            float off = 0.f;
+            for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
+            if (live) {
+                if (g == 0) out[path] = P.S0;
+                if (has_chunk) {
+                    float* o = out + (int64_t)(k0 + 1) * P.ld + path;
+                    const float* w = W + (size_t)k0 * TP + p;
+                    const int kend = min(k1, n);
+#pragma unroll 4
+                    for (int k = k0; k < kend; ++k, o += P.ld, w += TP) *o = P.S0 * fast_ex2(off + *w);
+                }
             }
         }
         __syncthreads();  // A / W / tot are rewritten by the next tile
@@ -373,12 +405,13 @@ int launch_tp(mcp_ctx* ctx, const RbParams& P, const PhiloxKeys& K, const float2
 // Host-side tables, all in double then rounded once to fp32.
 //   phi = DFT+(zero-pad(0.5 t^{2H}) to M = nextPow2(n+1))           RoughVolatility.cpp:212-236
 //   phis_k = phi_k * sqrt(2H) eta / M' * log2(e)                    (:270 pads to M' = nextPow2(n); :284 scale; :198-200 1/M')
-//   comp2_k = -0.5 eta^2 t_k^{2H} * log2(e)                         :304
-int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<float>& phis, std::vector<float>& tw,
+//   comp2_k = -0.5 eta^2 t_k^{2H} * log2(e) + log2(xi)              :304 (xi folded into the exponent)
+int mcp_rbergomi_tables(int n, double H, double eta, double dt, double xi, std::vector<float>& phis, std::vector<float>& tw,
                         std::vector<float>& comp2, std::vector<int>& rev, int* Mp_out, int* lgMp_out, int* lg_radix_out,
                         int* n_stage) {
     const int M = next_pow2(n + 1), Mp = next_pow2(n);
     const double log2e = 1.4426950408889634074;
+    const double log2_xi = xi > 0.0 ? log2(xi) : -INFINITY;  // xi = 0: v = 0 exactly, as xi exp(.) gives
     std::vector<double> lam(n + 1);
     for (int i = 0; i <= n; ++i) lam[i] = 0.5 * pow((double)i * dt, 2.0 * H);
     const double scale = sqrt(2.0 * H) * eta / (double)Mp * log2e;
@@ -401,7 +434,7 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, std::vector<floa
         tw[2 * q + 1] = (float)sin(ang);
     }
     comp2.assign((size_t)Mp, 0.f);
-    for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * pow((double)k * dt, 2.0 * H) * log2e);
+    for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * pow((double)k * dt, 2.0 * H) * log2e + log2_xi);
     int lg = 0;
     while ((1 << lg) < Mp) ++lg;
     int radix[8], ns = 0, rem = lg, packed = 0;
@@ -438,8 +471,8 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     const int n = ps->n_steps;
     if (n < 1) return mcp_fail(ctx, MCP_ERR_INVALID, "rbergomi: n_steps must be >= 1");
     if (n > 4096) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n_steps %d > 4096", n);
-    if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || fabs(prm->rho) > 1.0)
-        return mcp_fail(ctx, MCP_ERR_DOMAIN, "rbergomi: need dt > 0, H >= 0, |rho| <= 1");
+    if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0))
+        return mcp_fail(ctx, MCP_ERR_DOMAIN, "rbergomi: need dt > 0, H >= 0, |rho| <= 1, xi >= 0");
     MCP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (injected && dump) {  // the normals used ARE the injected ones
         memcpy(dump, injected, (size_t)ps->n_paths * 4 * n * sizeof(float));
@@ -450,12 +483,12 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     std::vector<int> pos;  // rev[]: storage position -> output index
     RbParams P;
     memset(&P, 0, sizeof(P));
-    mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, phis, tw, comp2, pos, &P.Mp, &P.lgMp, &P.lg_radix, &P.n_stage);
+    mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &P.Mp, &P.lgMp, &P.lg_radix, &P.n_stage);
     P.S0 = (float)prm->S0;
-    P.xi = (float)prm->xi;
-    P.r_dt = (float)(prm->r * prm->dt);
-    P.half_dt = (float)(0.5 * prm->dt);
-    P.sq_dt = (float)sqrt(prm->dt);
+    const double log2e = 1.4426950408889634074;
+    P.rd2 = (float)(prm->r * prm->dt * log2e);
+    P.nh2 = (float)(-0.5 * prm->dt * log2e);
+    P.lsq = (float)log2(sqrt(prm->dt) * log2e);
     P.rho = (float)prm->rho;
     P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);
     P.n = n;
