@@ -191,6 +191,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(rank, world, uid[0])
 
+    peer_mem = world > 1 and eng.comm_uses_peer_memory()
     ps = eng.pathset(n_loc, N_STEPS)
     model = dict(MODEL)
     lsm = dict(r=MODEL["r"], strike=STRIKE, maturity=MATURITY, dt=MODEL["dt"], is_call=False, poly_order=POLY, carry=carry)
@@ -299,7 +300,9 @@ def main():
                                    f"(BASELINE configs[2]); generate + price each step",
                        "paths_total": n_total, "paths_per_gpu": n_loc, "n_steps": N_STEPS, "poly_order": POLY,
                        "l2": "inputs exceed L2 (slab %.1f GB per GPU)" % (n_loc * (N_STEPS + 1) * 4 / 1e9),
-                       "parallelism": f"paths sharded x{world}; NCCL all-reduce of {3 * POLY + 2} fp64 moments per step"},
+                       "parallelism": (f"paths sharded x{world}; per-step all-reduce of {3 * POLY + 2} fp64 moments "
+                                       + ("inside the sweep kernel over NVLink peer memory (CUDA IPC mailboxes)" if peer_mem
+                                          else "by ncclAllReduce" if world > 1 else "(single GPU: none)"))},
             "time_to_price_s": ms_per_step * 1e-3, "lsm_price_time_s": lsm_ms_sum / args.steps * 1e-3,
             "price": price, "std_error": se,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -84,6 +84,9 @@ int mcp_get_profile(const mcp_ctx *ctx, mcp_profile *out);
 int mcp_comm_unique_id(void *id128);                                  /* rank 0: 128-byte ncclUniqueId */
 int mcp_comm_init(mcp_ctx *ctx, int rank, int nranks, const void *id128);
 int mcp_comm_info(const mcp_ctx *ctx, int *rank, int *nranks);
+/* 1 when the per-step moment exchange runs inside the sweep kernel over NVLink peer memory (one process per GPU,
+ * CUDA IPC mailboxes), 0 when it goes through ncclAllReduce (MCP_COMM_IMPL=nccl forces that) */
+int mcp_comm_uses_peer_memory(const mcp_ctx *ctx);
 
 /* ----------------------------------------------------------------------------------------- pathsets */
 int mcp_pathset_create(mcp_ctx *ctx, int64_t n_paths, int n_steps, int dtype, mcp_pathset **out);

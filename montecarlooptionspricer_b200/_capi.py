@@ -58,6 +58,7 @@ SIGNATURES = {
     "mcp_get_profile": (C.c_int, [_vp, C.POINTER(Profile)]),
     "mcp_comm_unique_id": (C.c_int, [_vp]),
     "mcp_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "mcp_comm_uses_peer_memory": (C.c_int, [_vp]),
     "mcp_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mcp_pathset_create": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.POINTER(_vp)]),
     "mcp_pathset_destroy": (C.c_int, [_vp]),

@@ -10,6 +10,16 @@
 
 struct McpNccl;  // dlopen'ed NCCL entry points (ctx.cu)
 
+// Mailbox layout: [parity 0|1][source rank][MCP_XROW doubles]; doubles 0..30 carry data, slot 31 the sequence flag.
+constexpr int MCP_XROW = 32;
+constexpr int MCP_XMAX_RANKS = 16;
+struct McpXchg {
+    int nranks = 1, rank = 0;
+    int enabled = 0;
+    double* const* peer = nullptr;  // device array [nranks]: mailbox base of every rank (own entry = local mailbox)
+    int* err = nullptr;             // device flag: set when a wait timed out
+};
+
 // One engine handle per host thread / per GPU rank.
 struct mcp_ctx {
     int device = 0;
@@ -24,6 +34,13 @@ struct mcp_ctx {
     // multi-GPU
     void* comm = nullptr;  // ncclComm_t
     int rank = 0, nranks = 1;
+    // peer-memory exchange (NVLink / NVSwitch P2P): every rank owns a small mailbox that all peers can store into,
+    // so the per-step moment all-reduce runs INSIDE the sweep kernel instead of as a separate NCCL launch
+    McpXchg xchg;
+    void* xchg_local = nullptr;            // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+    void* xchg_peer_ptrs_dev = nullptr;    // device copy of xchg.peer[]
+    std::vector<void*> xchg_opened;        // peers' mailboxes opened with cudaIpcOpenMemHandle
+    unsigned long long xchg_seq = 0;       // exchange counter (all ranks advance in lock step)
 
     // grow-only device scratch (regression partials, coefficient tables, transposition staging ...)
     void* scratch = nullptr;

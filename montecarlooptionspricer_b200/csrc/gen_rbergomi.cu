@@ -54,11 +54,6 @@ __device__ __forceinline__ float fast_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float fast_sqrt(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 struct RbParams;
 __device__ __forceinline__ float log2_increment(float e, float w, const RbParams& P);

@@ -71,6 +71,8 @@ struct SweepArgs {
     int solve_here;  // single GPU: the last CTA to finish also solves step j-1 (no extra launches)
     int64_t pin_paths;  // leading paths whose carry lines are kept L2-resident across sweeps
     int pin_mode;       // 1: evict_last hints, 2: plain accesses under a persisting access-policy window
+    McpXchg x;          // peer-memory mailboxes (multi-GPU): the moment all-reduce happens inside this kernel
+    unsigned long long seq;  // sequence number of this launch's exchange
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
@@ -511,9 +513,60 @@ __global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* 
     if (threadIdx.x == 0 && blockIdx.x == 0) solve_dispatch(mom, p, coef_row);
 }
 
+// All-reduce (sum) of `vals[0..NV)` across GPUs through the peer-memory mailboxes, executed by ONE CTA per rank (the
+// last one of its sweep launch).  One-shot all-gather: every rank stores its row into the mailbox of every rank
+// over NVLink (plain P2P stores), publishes a sequence flag with release semantics, waits until all rows of its own
+// mailbox carry that sequence, and adds them up IN RANK ORDER -- so every rank obtains the bitwise identical sum and
+// then solves the identical system.  Two mailbox halves (sequence parity) keep exchange s+1 from overwriting rows a
+// slow rank is still reading for exchange s.  A wait that exceeds ~20 s raises the error flag instead of hanging.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int NV>
+__device__ __forceinline__ void xchg_allreduce(const McpXchg& x, unsigned long long seq, double* vals /* shared [NV] */) {
+    static_assert(NV < MCP_XROW, "row too long for the mailbox");
+    const int tid = threadIdx.x, n = x.nranks;
+    const size_t half = (size_t)(seq & 1ull) * (size_t)n;
+    for (int idx = tid; idx < n * NV; idx += LSM_NT) {
+        const int r = idx / NV, k = idx - r * NV;
+        volatile double* row = x.peer[r] + (half + (size_t)x.rank) * MCP_XROW;
+        row[k] = vals[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < n) {
+        st_release_sys(reinterpret_cast<unsigned long long*>(x.peer[tid] + (half + (size_t)x.rank) * MCP_XROW + (MCP_XROW - 1)), seq);
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(x.peer[x.rank] + (half + (size_t)tid) * MCP_XROW + (MCP_XROW - 1));
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flag) < seq) {
+            if (global_ns() - t0 > 20000000000ull) { *x.err = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (tid < NV) {
+        const volatile double* mine = x.peer[x.rank] + half * MCP_XROW;
+        double s = 0.0;
+        for (int r = 0; r < n; ++r) s += mine[(size_t)r * MCP_XROW + tid];
+        vals[tid] = s;
+    }
+    __syncthreads();
+}
+
 // Epilogue of a sweep launch: per-CTA partial row, then the LAST CTA to finish (completion ticket) folds all rows
-// in a fixed order -- bitwise reproducible whichever CTA is last -- into `moments` (or the running sum of V0) and,
-// on a single GPU, solves step j-1 right here, so one time step is exactly one kernel launch.
+// in a fixed order -- bitwise reproducible whichever CTA is last -- into `moments` (or the running sum of V0),
+// all-reduces them across GPUs through the peer-memory mailboxes when those are up, and solves step j-1 right here,
+// so one time step is exactly one kernel launch (on one GPU and on many).
 template <int NV, int P>
 __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)[NV]) {
     __shared__ double red[8][32];
@@ -525,21 +578,34 @@ __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int k = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    double s = 0.0;
-    if (k < NV)
-        for (int b = grp; b < (int)gridDim.x; b += LSM_NT / 32) s += __ldcg(a.d.partial + (int64_t)b * MOM_LD + k);
-    red[grp][k] = s;
+    // fold gridDim.x rows in a FIXED order with as many independent loads in flight as possible: thread (seg, k) sums
+    // a contiguous block of rows for moment k, then thread k adds the NSEG block sums in order
+    constexpr int NSEG = LSM_NT / NV;
+    __shared__ double seg_sum[NSEG][NV];
+    const int rows = ((int)gridDim.x + NSEG - 1) / NSEG;
+    if (threadIdx.x < NSEG * NV) {
+        const int seg = threadIdx.x / NV, k = threadIdx.x - seg * NV;
+        const int b0 = seg * rows, b1 = min(b0 + rows, (int)gridDim.x);
+        double s = 0.0;
+#pragma unroll 8
+        for (int b = b0; b < b1; ++b) s += __ldcg(a.d.partial + (int64_t)b * MOM_LD + k);
+        seg_sum[seg][k] = s;
+    }
     __syncthreads();
-    double* out = a.do_final ? a.d.fin : a.d.moments;
     if (threadIdx.x < NV) {
         double t = 0.0;
 #pragma unroll
-        for (int g = 0; g < LSM_NT / 32; ++g) t += red[g][threadIdx.x];
+        for (int g = 0; g < NSEG; ++g) t += seg_sum[g][threadIdx.x];
         red[0][threadIdx.x] = t;
-        if (!a.do_final || threadIdx.x == 0) out[threadIdx.x] = t;
     }
+    if (a.do_final && threadIdx.x == 1) red[0][1] = (double)a.n;  // the final exchange carries {sum V0, N}
     __syncthreads();
+    if (a.x.enabled) xchg_allreduce<NV>(a.x, a.seq, &red[0][0]);
+    if (a.do_final) {
+        if (threadIdx.x == 0) { a.d.fin[0] = red[0][0]; if (a.x.enabled) a.d.fin[2] = red[0][1]; }
+    } else if (threadIdx.x < NV) {
+        a.d.moments[threadIdx.x] = red[0][threadIdx.x];
+    }
     if (threadIdx.x == 0) {
         *a.d.counter = 0u;
         if (a.do_moments && a.solve_here) solve_normal_equations<P>(&red[0][0], a.d.coef + (int64_t)(a.j - 1) * COEF_LD);
@@ -770,7 +836,10 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     memset(&a, 0, sizeof(a));
     a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
     a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
-    a.solve_here = (ctx->nranks <= 1 || !ctx->comm) ? 1 : 0;
+    const bool multi = ctx->nranks > 1 && ctx->comm;
+    const bool p2p = multi && ctx->xchg.enabled;
+    if (p2p) a.x = ctx->xchg;
+    a.solve_here = (!multi || p2p) ? 1 : 0;
     a.pin_paths = ((int64_t)env_int("MCP_SWEEP_PIN_MB", 0) << 20) / 4 / 8 * 8;  // carry bytes kept L2-resident
     a.pin_mode = env_int("MCP_SWEEP_PIN_MODE", 1);
     if (a.pin_paths > N) a.pin_paths = N / 8 * 8;
@@ -802,6 +871,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         a.terminal = (j == M - 1);
         a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
         a.do_final = (j == 0);
+        if (p2p && (a.do_moments || a.do_final)) a.seq = ++ctx->xchg_seq;
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j), st);
         sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
         MCP_LAUNCH_CHECK(ctx);
@@ -821,8 +891,8 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
     const double nloc = (double)N;
-    MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
-    MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below
+    if (!p2p) MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
+    if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
     if (prm->carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
     else lsm_sqdev_kernel<double><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
     MCP_LAUNCH_CHECK(ctx);
@@ -845,8 +915,11 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         MCP_CUDA(ctx, cudaMemcpyAsync(hmu.data(), d.mu, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
         MCP_CUDA(ctx, cudaMemcpyAsync(his.data(), d.inv_s, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
     }
+    int xerr = 0;
+    if (p2p) MCP_CUDA(ctx, cudaMemcpyAsync(&xerr, ctx->xchg.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     MCP_CUDA(ctx, cudaGetLastError());
+    if (xerr) return mcp_fail(ctx, MCP_ERR_NCCL, "lsm: peer-memory moment exchange timed out (a rank did not reach the same sweep step)");
 
     const double ng = fin[2];
     res->sum_v0 = fin[0];

@@ -105,6 +105,9 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128)
         self._chk(self._L.mcp_comm_init(self._h, rank, nranks, buf))
 
+    def comm_uses_peer_memory(self) -> bool:
+        return bool(self._L.mcp_comm_uses_peer_memory(self._h))
+
     def comm_info(self):
         r, n = C.c_int(), C.c_int()
         self._chk(self._L.mcp_comm_info(self._h, C.byref(r), C.byref(n)))
