@@ -76,9 +76,9 @@ struct SweepArgs {
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
-template <int NV>
+template <int NV, int NT = LSM_NT>
 __device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NV], double* __restrict__ partial_row) {
-    __shared__ double red[LSM_NT / 32][NV];
+    __shared__ double red[NT / 32][NV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -89,13 +89,13 @@ __device__ __forceinline__ void block_reduce_to_partial(double (&acc)[NV], doubl
     if (threadIdx.x < NV) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < LSM_NT / 32; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < NT / 32; ++w) s += red[w][threadIdx.x];
         partial_row[threadIdx.x] = s;
     }
 }
 
 struct SweepArgs;
-template <int NV, int P>
+template <int NV, int P, int NT = 256>
 __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)[NV]);
 
 template <typename T>
@@ -361,19 +361,18 @@ struct FastConsts {
     float2 d_hi, d_lo;            // e^{-r dt} as a two-float product
 };
 
-// One group of 8 consecutive paths.  TAIL: the (single) ragged last group, lanes >= nvalid are masked out.
+// Arithmetic of one group of 8 paths held in registers: s8 = S_j, p8 = S_{j-1}, v8 = carry (updated in place).
+// Path e of the group is global path idx[e >> 2] + (e & 3), i.e. two runs of four consecutive paths (the direct-load
+// kernel uses one run of eight: idx1 = idx0 + 4).  TAIL: the ragged last group, paths >= a.n are masked out.
 template <int P, bool TAU, bool TAIL>
-__device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts<P>& k, const float* __restrict__ Sj, const float* __restrict__ Sp,
-                                            float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
-    const bool pinned = i0 < a.pin_paths;
-    const F8 s8 = ld8_stream(Sj + i0);
-    F8 p8 = s8, v8 = s8;
-    if (a.do_moments) p8 = ld8_keep(Sp + i0);
-    if (mode != 2) v8 = pinned ? (a.pin_mode == 2 ? ld8_keep(V + i0) : ld8_pinned(V + i0)) : ld8_stream(V + i0);
+__device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastConsts<P>& k, const F8& s8, const F8& p8, F8& v8, int64_t idx0, int64_t idx1,
+                                              int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
     const float2(&s)[4] = s8.q;
     const float2(&sp)[4] = p8.q;
     float2(&v)[4] = v8.q;
-    const int nvalid = TAIL ? (int)(a.n - i0) : 8;
+    bool ok[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ok[e] = !TAIL || ((e < 4 ? idx0 : idx1) + (e & 3) < a.n);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float2 pay = __fadd2_rn(__ffma2_rn(s[q], k.sg, k.nsK), k.nsKlo);  // include/core/common.h:8-14
@@ -394,22 +393,21 @@ __device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts
                 v[q].x = pay.x > 1e-14f ? fmaxf(pay.x, cont.x) : (pay.x < 1e-14f ? vd.x : 0.f);
                 v[q].y = pay.y > 1e-14f ? fmaxf(pay.y, cont.y) : (pay.y < 1e-14f ? vd.y : 0.f);
                 if (TAU) {
-                    if (pay.x > 1e-14f && !(pay.x < cont.x) && 2 * q < nvalid) a.tau[i0 + 2 * q] = a.j;
-                    if (pay.y > 1e-14f && !(pay.y < cont.y) && 2 * q + 1 < nvalid) a.tau[i0 + 2 * q + 1] = a.j;
+                    const int64_t ib = (q < 2 ? idx0 : idx1) + 2 * (q & 1);
+                    if (pay.x > 1e-14f && !(pay.x < cont.x) && ok[2 * q]) a.tau[ib] = a.j;
+                    if (pay.y > 1e-14f && !(pay.y < cont.y) && ok[2 * q + 1]) a.tau[ib + 1] = a.j;
                 }
             }
         }
     }
-    if (pinned) { if (a.pin_mode == 2) st8_keep(V + i0, v8); else st8_pinned(V + i0, v8); }
-    else st8_stream(V + i0, v8);
     if (a.do_moments) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float2 pp = __fadd2_rn(__ffma2_rn(sp[q], k.sg, k.nsK), k.nsKlo);  // payoff of step j-1 (sign test only)
             float2 m = make_float2(pp.x > 1e-14f ? 1.f : 0.f, pp.y > 1e-14f ? 1.f : 0.f);  // LSMPricer.cpp:51-58
             if (TAIL) {
-                if (2 * q >= nvalid) m.x = 0.f;
-                if (2 * q + 1 >= nvalid) m.y = 0.f;
+                if (!ok[2 * q]) m.x = 0.f;
+                if (!ok[2 * q + 1]) m.y = 0.f;
             }
             const float2 x = __fmul2_rn(__fmul2_rn(__fadd2_rn(sp[q], k.nmu_p), k.is_p), m);
             const float2 y = __fmul2_rn(__ffma2_rn(v[q], k.d_lo, __fmul2_rn(v[q], k.d_hi)), m);  // LSMPricer.cpp:69
@@ -429,26 +427,30 @@ __device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts
         for (int q = 0; q < 4; ++q) {
             float2 w = v[q];
             if (TAIL) {
-                if (2 * q >= nvalid) w.x = 0.f;
-                if (2 * q + 1 >= nvalid) w.y = 0.f;
+                if (!ok[2 * q]) w.x = 0.f;
+                if (!ok[2 * q + 1]) w.y = 0.f;
             }
             la[0] = __fadd2_rn(la[0], w);
         }
     }
 }
 
-template <int P, bool TAU, int OCC>
-__global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs a) {
-    constexpr int NM = 3 * P + 2;
-    constexpr int NV = NM > 2 ? NM : 2;
-    constexpr int FLUSH = 8;  // groups (x8 paths) between fp32 -> fp64 folds
-    __shared__ double sacc[NV][LSM_NT];
-    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
-    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
-    float* __restrict__ V = reinterpret_cast<float*>(a.V);
-    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+// Direct-load form: one group = 8 consecutive paths, 256-bit loads / stores with L2 eviction priorities.
+template <int P, bool TAU, bool TAIL>
+__device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts<P>& k, const float* __restrict__ Sj, const float* __restrict__ Sp,
+                                            float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+    const bool pinned = i0 < a.pin_paths;
+    const F8 s8 = ld8_stream(Sj + i0);
+    F8 p8 = s8, v8 = s8;
+    if (a.do_moments) p8 = ld8_keep(Sp + i0);
+    if (mode != 2) v8 = pinned ? (a.pin_mode == 2 ? ld8_keep(V + i0) : ld8_pinned(V + i0)) : ld8_stream(V + i0);
+    fast2_compute<P, TAU, TAIL>(a, k, s8, p8, v8, i0, i0 + 4, mode, la);
+    if (pinned) { if (a.pin_mode == 2) st8_keep(V + i0, v8); else st8_pinned(V + i0, v8); }
+    else st8_stream(V + i0, v8);
+}
 
-    FastConsts<P> k;
+template <int P>
+__device__ __forceinline__ void fast2_load_consts(const SweepArgs& a, FastConsts<P>& k) {
 #pragma unroll
     for (int m = 0; m <= P; ++m) k.c[m] = splat2((float)a.d.coef[(int64_t)a.j * COEF_LD + m]);
     k.nmu = splat2(-(float)a.d.mu[a.j]);
@@ -463,6 +465,21 @@ __global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs 
     const float d_hi = (float)a.disc;
     k.d_hi = splat2(d_hi);
     k.d_lo = splat2((float)(a.disc - (double)d_hi));
+}
+
+template <int P, bool TAU, int OCC>
+__global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs a) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    constexpr int FLUSH = 8;  // groups (x8 paths) between fp32 -> fp64 folds
+    __shared__ double sacc[NV][LSM_NT];
+    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    float* __restrict__ V = reinterpret_cast<float*>(a.V);
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+
+    FastConsts<P> k;
+    fast2_load_consts<P>(a, k);
 
     float2 la[NV];
 #pragma unroll
@@ -488,6 +505,144 @@ __global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs 
 #pragma unroll
         for (int m = 0; m < NV; ++m) acc[m] = sacc[m][threadIdx.x] + ((double)la[m].x + (double)la[m].y);
         sweep_epilogue<NV, P>(a, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep(j), THROUGHPUT kernel v3: the same arithmetic fed by a TMA ring.
+// ncu on v2 (profiles/r01f): 56% of the stall samples are long-scoreboard waits and DRAM is 65% busy -- with 24
+// resident warps per SM the direct loads cannot keep enough bytes in flight.  Here one persistent CTA per SM
+// (512 threads) streams tiles of 4096 paths through a ring of shared-memory stages filled by bulk async copies
+// (cp.async.bulk / UBLKCP, completion on an mbarrier): memory-level parallelism is set by the ring depth
+// (up to 3 x 48 KB in flight per SM), not by registers or occupancy.  S_j and V tiles are fetched with an
+// L2 evict-first policy (touched once per sweep), S_{j-1} with the default policy (it is next sweep's S_j).
+// Thread t owns paths [4t, 4t+4) and [2048+4t, 2048+4t+4) of a tile: conflict-free LDS.128, coalesced STG.128.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TMA_NT = 512;
+constexpr int TMA_TILE = 4096;                                  // paths per tile
+constexpr int TMA_STAGE_BYTES = 3 * TMA_TILE * 4;               // S_j | S_{j-1} | V
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void stg4_stream(float* p, float2 a, float2 b) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+
+template <int P, bool TAU>
+__global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, int n_stages) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    constexpr int FLUSH = 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES);
+    double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES + 128);  // [NV][TMA_NT]
+    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    float* __restrict__ V = reinterpret_cast<float*>(a.V);
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int st = 0; st < n_stages; ++st) mbar_init(full + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    FastConsts<P> k;
+    fast2_load_consts<P>(a, k);
+    float2 la[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * TMA_NT + tid] = 0.0; }
+    __syncthreads();
+
+    const int64_t ntile = (a.n + TMA_TILE - 1) / TMA_TILE;
+    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint64_t pol = l2_policy_evict_first();
+    // tile `it` of this CTA, in serpentine order (what the previous sweep touched last is read first)
+    auto tile_of = [&](int64_t it) -> int64_t {
+        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
+        return (a.j & 1) ? (ntile - 1 - t) : t;
+    };
+    auto issue = [&](int64_t it) {  // one elected thread: arm the stage's barrier and start its bulk copies
+        const int st = (int)(it % n_stages);
+        const int64_t i0 = tile_of(it) * TMA_TILE;
+        const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;  // rows are padded to ld (multiple of 128)
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        float* dst = ring + (size_t)st * (3 * TMA_TILE);
+        mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (mode != 2 ? 1u : 0u)));
+        bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
+        if (a.do_moments) bulk_g2s(dst + TMA_TILE, Sp + i0, bytes, full + st);
+        if (mode != 2) bulk_g2s_hint(dst + 2 * TMA_TILE, V + i0, bytes, full + st, pol);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it);
+
+    int since = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int st = (int)(it % n_stages);
+        const uint32_t parity = (uint32_t)((it / n_stages) & 1);
+        while (!mbar_try_wait(full + st, parity)) {}
+        const float* buf = ring + (size_t)st * (3 * TMA_TILE);
+        F8 s8, p8, v8;
+        {
+            const float4 x0 = *reinterpret_cast<const float4*>(buf + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2048 + 4 * tid);
+            s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
+        }
+        p8 = s8; v8 = s8;
+        if (a.do_moments) {
+            const float4 x0 = *reinterpret_cast<const float4*>(buf + TMA_TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + TMA_TILE + 2048 + 4 * tid);
+            p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
+        }
+        if (mode != 2) {
+            const float4 x0 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 2048 + 4 * tid);
+            v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
+        }
+        __syncthreads();  // every thread holds its part of the stage in registers: the slot can be refilled
+        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages);
+
+        const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = i0 + 2048 + 4 * tid;
+        if (i0 + TMA_TILE <= a.n) fast2_compute<P, TAU, false>(a, k, s8, p8, v8, ia, ib, mode, la);
+        else fast2_compute<P, TAU, true>(a, k, s8, p8, v8, ia, ib, mode, la);
+        if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
+        if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+        if (++since == FLUSH) {
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                sacc[m * TMA_NT + tid] += (double)(la[m].x + la[m].y);
+                la[m] = make_float2(0.f, 0.f);
+            }
+            since = 0;
+        }
+    }
+    if (a.do_moments || a.do_final) {
+        double acc[NV];
+#pragma unroll
+        for (int m = 0; m < NV; ++m) acc[m] = sacc[m * TMA_NT + tid] + (double)(la[m].x + la[m].y);
+        sweep_epilogue<NV, P, TMA_NT>(a, acc);
     }
 }
 
@@ -533,12 +688,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-template <int NV>
+template <int NV, int NT>
 __device__ __forceinline__ void xchg_allreduce(const McpXchg& x, unsigned long long seq, double* vals /* shared [NV] */) {
     static_assert(NV < MCP_XROW, "row too long for the mailbox");
     const int tid = threadIdx.x, n = x.nranks;
     const size_t half = (size_t)(seq & 1ull) * (size_t)n;
-    for (int idx = tid; idx < n * NV; idx += LSM_NT) {
+    for (int idx = tid; idx < n * NV; idx += NT) {
         const int r = idx / NV, k = idx - r * NV;
         volatile double* row = x.peer[r] + (half + (size_t)x.rank) * MCP_XROW;
         row[k] = vals[k];
@@ -567,11 +722,11 @@ __device__ __forceinline__ void xchg_allreduce(const McpXchg& x, unsigned long l
 // in a fixed order -- bitwise reproducible whichever CTA is last -- into `moments` (or the running sum of V0),
 // all-reduces them across GPUs through the peer-memory mailboxes when those are up, and solves step j-1 right here,
 // so one time step is exactly one kernel launch (on one GPU and on many).
-template <int NV, int P>
+template <int NV, int P, int NT>
 __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)[NV]) {
     __shared__ double red[8][32];
     __shared__ bool is_last;
-    block_reduce_to_partial<NV>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
+    block_reduce_to_partial<NV, NT>(acc, a.d.partial + (int64_t)blockIdx.x * MOM_LD);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(a.d.counter, 1u) == gridDim.x - 1);
@@ -580,7 +735,7 @@ __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)
     __threadfence();
     // fold gridDim.x rows in a FIXED order with as many independent loads in flight as possible: thread (seg, k) sums
     // a contiguous block of rows for moment k, then thread k adds the NSEG block sums in order
-    constexpr int NSEG = LSM_NT / NV;
+    constexpr int NSEG = NT / NV;
     __shared__ double seg_sum[NSEG][NV];
     const int rows = ((int)gridDim.x + NSEG - 1) / NSEG;
     if (threadIdx.x < NSEG * NV) {
@@ -600,7 +755,7 @@ __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)
     }
     if (a.do_final && threadIdx.x == 1) red[0][1] = (double)a.n;  // the final exchange carries {sum V0, N}
     __syncthreads();
-    if (a.x.enabled) xchg_allreduce<NV>(a.x, a.seq, &red[0][0]);
+    if (a.x.enabled) xchg_allreduce<NV, NT>(a.x, a.seq, &red[0][0]);
     if (a.do_final) {
         if (threadIdx.x == 0) { a.d.fin[0] = red[0][0]; if (a.x.enabled) a.d.fin[2] = red[0][1]; }
     } else if (threadIdx.x < NV) {
@@ -678,6 +833,7 @@ __global__ void lsm_fill_tau_kernel(int32_t* __restrict__ tau, int64_t n, int32_
 }
 
 typedef void (*SweepFn)(SweepArgs);
+typedef void (*SweepFn2)(SweepArgs, int);
 
 template <typename ST, typename CT>
 SweepFn pick_sweep(int p) {
@@ -714,6 +870,19 @@ SweepFn pick_sweep_fast2(int p) {
         case 4: return lsm_sweep_fast2_kernel<4, TAU, OCC>;
         case 5: return lsm_sweep_fast2_kernel<5, TAU, OCC>;
         default: return lsm_sweep_fast2_kernel<6, TAU, OCC>;
+    }
+}
+
+template <bool TAU>
+SweepFn2 pick_sweep_tma(int p) {
+    switch (p) {
+        case 0: return lsm_sweep_tma_kernel<0, TAU>;
+        case 1: return lsm_sweep_tma_kernel<1, TAU>;
+        case 2: return lsm_sweep_tma_kernel<2, TAU>;
+        case 3: return lsm_sweep_tma_kernel<3, TAU>;
+        case 4: return lsm_sweep_tma_kernel<4, TAU>;
+        case 5: return lsm_sweep_tma_kernel<5, TAU>;
+        default: return lsm_sweep_tma_kernel<6, TAU>;
     }
 }
 
@@ -787,6 +956,24 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     int64_t grid = (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4);
     const int64_t cap = (int64_t)ctx->sm_count * occ;
     if (grid > cap) grid = cap;
+    // TMA-ring kernel (one persistent 512-thread CTA per SM) once there are enough 4096-path tiles to feed every SM
+    SweepFn2 sweep_tma = nullptr;
+    int tma_stages = 0;
+    size_t tma_smem = 0;
+    const int64_t ntile = (N + TMA_TILE - 1) / TMA_TILE;
+    if (ps->dtype == MCP_F32 && prm->carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
+        const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
+        const size_t fixed = 128 + (size_t)nv * TMA_NT * 8;
+        tma_stages = (int)((227u * 1024u - 8192u - fixed) / TMA_STAGE_BYTES);  // 8 KB: the kernel's static shared memory
+        const int want = env_int("MCP_SWEEP_STAGES", 0);
+        if (want > 0 && want < tma_stages) tma_stages = want;
+        if (tma_stages >= 2) {
+            sweep_tma = first_exercise ? pick_sweep_tma<true>(p) : pick_sweep_tma<false>(p);
+            tma_smem = (size_t)tma_stages * TMA_STAGE_BYTES + fixed;
+            MCP_CUDA(ctx, cudaFuncSetAttribute(sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+            grid = ctx->sm_count < ntile ? ctx->sm_count : ntile;
+        }
+    }
 
     // ---- workspace ----
     size_t off = 0;
@@ -873,7 +1060,8 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         a.do_final = (j == 0);
         if (p2p && (a.do_moments || a.do_final)) a.seq = ++ctx->xchg_seq;
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j), st);
-        sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
+        if (sweep_tma) sweep_tma<<<(unsigned)grid, TMA_NT, tma_smem, st>>>(a, tma_stages);
+        else sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
         MCP_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j + 1), st);
         if (a.do_moments && !a.solve_here) {  // multi-GPU: global moments, then every rank solves the same system

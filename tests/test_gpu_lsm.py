@@ -185,3 +185,27 @@ def test_price_rbergomi_lsm_native_within_3se_of_oracle(engine, port):
     se = np.hypot(out.std_error, want["stderr"])
     assert abs(out.price - want["price"]) < 3 * se, (out.price, want["price"], se)
     assert out.n_paths_global == 1 << 15 and gen_ms > 0
+
+
+def test_lsm_tma_ring_kernel_matches_direct_kernel_and_oracle(engine, port, monkeypatch):
+    """The TMA-ring sweep (persistent 512-thread CTAs, bulk async copies into a shared-memory ring) takes over once
+    there are >= 2 tiles of 4096 paths per SM.  Ragged path count (tail tile), put and call, with first-exercise
+    output: same price as the direct-load kernel to fp32-accumulation noise, and both within the stated 1e-5 of the
+    fp64 oracle on the same fp32 path values."""
+    n_paths, n = 2 * 148 * 4096 + 4096 * 3 + 77, 12
+    ps = engine.pathset(n_paths, n)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.2, 1.0 / n, seed=5)
+    slab = ps.download_timemajor()
+    for is_call, K in ((False, 100.0), (True, 97.0)):
+        want = port.lsm_timemajor_f32(slab, 0.05, K, 1.0, 1.0 / n, is_call, 3)
+        got = {}
+        for impl in ("3", "2"):
+            monkeypatch.setenv("MCP_SWEEP_IMPL", impl)
+            got[impl] = engine.lsm_price(ps, 0.05, K, 1.0, 1.0 / n, is_call, 3, carry=m.MCP_F32, want_first_exercise=(impl == "3"), want_v0=True)
+            assert abs(got[impl].price - want["price"]) < 1e-5 * want["price"], (impl, got[impl].price, want["price"])
+            assert abs(got[impl].std_error - want["stderr"]) < 1e-4 * want["stderr"] + 1e-9 * want["price"]  # call: V0 is one constant
+        assert abs(got["3"].price - got["2"].price) < 2e-7 * want["price"]
+        assert np.max(np.abs(got["3"].v0 - got["2"].v0)) < 1e-4  # same per-path values up to decisions at fp32 near-ties
+        agree = np.mean(got["3"].first_exercise == want["first_ex"])
+        assert agree > 0.9999, agree  # fp32 decisions differ from the fp64 oracle at near-ties only
+    ps.close()
