@@ -956,6 +956,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     int64_t grid = (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4);
     const int64_t cap = (int64_t)ctx->sm_count * occ;
     if (grid > cap) grid = cap;
+    const int64_t grid_aux = grid;  // the small streaming kernels keep the occupancy-sized grid
     // TMA-ring kernel (one persistent 512-thread CTA per SM) once there are enough 4096-path tiles to feed every SM
     SweepFn2 sweep_tma = nullptr;
     int tma_stages = 0;
@@ -979,7 +980,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_coef = take((size_t)M * COEF_LD * 8), o_mu = take((size_t)M * 8), o_is = take((size_t)M * 8);
-    const size_t o_ssum = take((size_t)M * 4 * 8), o_part = take((size_t)grid * MOM_LD * 8), o_mom = take(MOM_LD * 8);
+    const size_t o_ssum = take((size_t)M * 4 * 8), o_part = take((size_t)(grid > grid_aux ? grid : grid_aux) * MOM_LD * 8), o_mom = take(MOM_LD * 8);
     const size_t o_fin = take(4 * 8), o_kind = take((size_t)M * 4), o_cnt = take(4);
     MCP_TRY(mcp_scratch_reserve(ctx, off));
     const size_t v_bytes = (size_t)mcp_round_up(N, 128) * csz;
@@ -1081,10 +1082,10 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     const double nloc = (double)N;
     if (!p2p) MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
     if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
-    if (prm->carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
-    else lsm_sqdev_kernel<double><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
+    if (prm->carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
+    else lsm_sqdev_kernel<double><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
     MCP_LAUNCH_CHECK(ctx);
-    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid, 1, d.fin + 1);
+    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid_aux, 1, d.fin + 1);
     MCP_LAUNCH_CHECK(ctx);
     MCP_TRY(mcp_allreduce_f64(ctx, d.fin + 1, 1));
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
