@@ -17,6 +17,7 @@
  *   mcp_lsm_price_host_rows     the same call, bound directly to host rows  src/core/PredictionGen.cpp:790
  *   mcp_estimate_rbergomi_params  RoughVolatility::estimateXi/H/Eta/Rho     src/models/RoughVolatility.cpp:72-169, :324-331
  *   mcp_generate_stock_price_paths  GenerateStockPricePaths, exact call shape  src/core/PredictionGen.cpp:736-737
+ *   mcp_price_surface_rbergomi_lsm  [new] the row loop of src/core/PredictionGen.cpp:542-866 for a strike x maturity grid
  *   mcp_asymptotic_price        AsymptoticAnalysis::PredictOptionPrice      include/models/AsymptoticAnalysisPricer.h:8-15
  *   mcp_martingale_price        MartingaleOptimization::PredictOptionPrice  include/models/MartingaleOptimizationPricer.h:10-18
  *   mcp_branching_price         BranchingProcesses::PredictOptionPrice      include/models/BranchingProcessPricer.h:8-16
@@ -159,6 +160,18 @@ int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_p
 int mcp_price_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *model, const mcp_lsm_params *lsm,
                            int64_t n_paths, int n_steps, uint64_t seed, uint64_t path_offset,
                            mcp_lsm_result *res, float *gen_ms);
+
+/* ---------------------------------------------------------------- batched strike x maturity surface (config 5)
+ * prices[m][k] (row-major [n_maturities][n_strikes]) = LSM price of strike k at maturity m under the rough-vol model:
+ * one path slab of n_paths x floor(T_m * steps_per_year) steps per maturity (PredictionGen.cpp:718), shared by all
+ * strikes.  Only maturities mat_first, mat_first + mat_stride, ... are priced (the others' entries are left alone):
+ * contracts are independent, so ranks split maturities with no collective.  lsm_tmpl supplies r, is_call,
+ * poly_order, basis, carry; its strike / maturity / dt are ignored (dt = model->dt). */
+int mcp_price_surface_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *model, const mcp_lsm_params *lsm_tmpl,
+                                   const double *strikes, int n_strikes, const double *maturities, int n_maturities,
+                                   int steps_per_year, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                                   int mat_first, int mat_stride, double *prices, double *std_errors /*nullable*/,
+                                   float *gen_ms_total /*nullable*/, float *lsm_ms_total /*nullable*/);
 
 /* ------------------------------------------------------------- exact-signature generator
  * Host estimators of the reference (pure host arithmetic, no device needed): xi = var(logret)/dt, H = DFA slope

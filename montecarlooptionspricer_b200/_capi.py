@@ -78,6 +78,8 @@ SIGNATURES = {
                                           C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "mcp_price_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), C.c_int64, C.c_int,
                                          C.c_uint64, C.c_uint64, C.POINTER(LsmResult), _fp]),
+    "mcp_price_surface_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), _dp, C.c_int, _dp, C.c_int,
+                                                 C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp, _dp, _fp, _fp]),
     "mcp_estimate_rbergomi_params": (C.c_int, [_dp, C.c_int64, C.POINTER(RbergomiParams)]),
     "mcp_generate_stock_price_paths": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                                  C.POINTER(_dp)]),

@@ -38,7 +38,7 @@ namespace {
 constexpr int NT = 512;  // threads per CTA: 16 warps share one 32-path tile; 2 CTAs/SM -> 32 resident warps
 
 struct RbParams {
-    float S0, rd2, nh2, lsq, rho, rho_c;  // r dt log2e, -dt/2 log2e, log2(sqrt(dt) log2e), rho, sqrt(1-rho^2)
+    float S0, rd2, nkq, lsq, rho, rho_c;  // r dt log2e, -1/(2 log2e), log2(sqrt(dt) log2e), rho, sqrt(1-rho^2)
     int n;        // steps
     int Mp;       // DFT length = nextPow2(n)
     int lgMp;     // log2(Mp)
@@ -127,12 +127,13 @@ __device__ __forceinline__ void dftR(float2 (&x)[R]) {
     }
 }
 
-// Log2-increment of one step from e = log2 v = X log2e + log2 xi - eta^2 t^{2H} log2e / 2 (tables carry the constants):
-//   v = 2^e,  sqrt(v) sqrt(dt) log2e = 2^{e/2 + lsq}  (v > 0 always, so the reference's max(0, v) is vacuous, :362),
-//   d = ((r - v/2) dt + sqrt(v) sqrt(dt) dW) log2e                                     RoughVolatility.cpp:356-363
+// Log2-increment of one step from e = log2 v = X log2e + log2 xi - eta^2 t^{2H} log2e / 2 (tables carry the constants).
+// One SFU op: u = sqrt(v) sqrt(dt) log2e = 2^{e/2 + lsq}  (v > 0 always, so the reference's max(0, v) is vacuous, :362);
+// then v dt log2e / 2 = u^2 kq with kq = 1 / (2 log2e), and
+//   d = ((r - v/2) dt + sqrt(v) sqrt(dt) dW) log2e = rd2 + u (w - kq u)                     RoughVolatility.cpp:356-363
 __device__ __forceinline__ float log2_increment(float e, float w, const RbParams& P) {
-    const float v = fast_ex2(e), sv = fast_ex2(fmaf(e, 0.5f, P.lsq));
-    return fmaf(sv, w, fmaf(v, P.nh2, P.rd2));
+    const float u = fast_ex2(fmaf(e, 0.5f, P.lsq));
+    return fmaf(u, fmaf(u, P.nkq, w), P.rd2);
 }
 
 // One DIF pass of radix R = 2^LGR over sub-transforms of length L = 2^lgL, for the TP paths of the tile.
@@ -636,7 +637,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     P.S0 = (float)prm->S0;
     const double log2e = 1.4426950408889634074;
     P.rd2 = (float)(prm->r * prm->dt * log2e);
-    P.nh2 = (float)(-0.5 * prm->dt * log2e);
+    P.nkq = (float)(-0.5 / log2e);
     P.lsq = (float)log2(sqrt(prm->dt) * log2e);
     P.rho = (float)prm->rho;
     P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);

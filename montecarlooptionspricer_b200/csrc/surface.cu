@@ -1,0 +1,68 @@
+// surface.cu -- batched strike x maturity sweep under rough-volatility LSM (BASELINE config 5).
+//
+// The reference prices one contract per CSV row, regenerating paths for every row (src/core/PredictionGen.cpp:718-737,
+// steps = floor(maturity * 252), 250 paths).  A surface of C = n_maturities x n_strikes contracts on the same
+// underlying shares its paths per maturity: one slab of n_paths x floor(T_m * steps_per_year) steps is generated per
+// maturity and every strike is priced on it by the fused LSM sweep, so generation is paid n_maturities times, not C.
+// Contracts are independent, hence the multi-GPU split needs NO collective: rank g prices maturities
+// g, g + G, g + 2G, ... (mat_first / mat_stride) with its own un-sharded path set (pass a ctx WITHOUT a communicator;
+// with one attached, paths are sharded instead and every contract's regression is global).
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_params* model, const mcp_lsm_params* lsm_tmpl, const double* strikes,
+                                              int n_strikes, const double* maturities, int n_maturities, int steps_per_year, int64_t n_paths,
+                                              uint64_t seed, uint64_t path_offset, int mat_first, int mat_stride, double* prices,
+                                              double* std_errors, float* gen_ms_total, float* lsm_ms_total) {
+    if (!ctx || !model || !lsm_tmpl || !strikes || !maturities || !prices) return MCP_ERR_INVALID;
+    if (n_strikes <= 0 || n_maturities <= 0 || steps_per_year <= 0 || n_paths <= 0 || mat_first < 0 || mat_stride <= 0)
+        return mcp_fail(ctx, MCP_ERR_INVALID, "surface: bad sizes");
+    float gen_total = 0.f, lsm_total = 0.f;
+    cudaEvent_t e0, e1;
+    MCP_CUDA(ctx, cudaEventCreate(&e0));
+    MCP_CUDA(ctx, cudaEventCreate(&e1));
+    int rc = MCP_OK;
+    for (int mi = mat_first; mi < n_maturities && rc == MCP_OK; mi += mat_stride) {
+        const double T = maturities[mi];
+        const int n_steps = (int)floor(T * (double)steps_per_year);  // PredictionGen.cpp:718
+        if (n_steps < 1) {  // PredictionGen.cpp:720-733 skips such rows and writes zeros
+            for (int k = 0; k < n_strikes; ++k) {
+                prices[(size_t)mi * n_strikes + k] = 0.0;
+                if (std_errors) std_errors[(size_t)mi * n_strikes + k] = 0.0;
+            }
+            continue;
+        }
+        mcp_pathset* ps = nullptr;
+        rc = mcp_pathset_create(ctx, n_paths, n_steps, MCP_F32, &ps);
+        if (rc != MCP_OK) break;
+        cudaEventRecord(e0, ctx->stream);
+        rc = mcp_gen_rbergomi(ctx, ps, model, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(mi + 1), path_offset, nullptr, nullptr);
+        cudaEventRecord(e1, ctx->stream);
+        for (int k = 0; k < n_strikes && rc == MCP_OK; ++k) {
+            mcp_lsm_params prm = *lsm_tmpl;
+            prm.strike = strikes[k];
+            prm.maturity = T;
+            prm.dt = model->dt;
+            mcp_lsm_result res;
+            rc = mcp_lsm_price(ctx, ps, &prm, &res, nullptr, nullptr, nullptr);
+            if (rc == MCP_OK) {
+                prices[(size_t)mi * n_strikes + k] = res.price;
+                if (std_errors) std_errors[(size_t)mi * n_strikes + k] = res.std_error;
+                lsm_total += res.elapsed_ms;
+            }
+        }
+        if (rc == MCP_OK) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) gen_total += ms;
+        }
+        mcp_pathset_destroy(ps);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (gen_ms_total) *gen_ms_total = gen_total;
+    if (lsm_ms_total) *lsm_ms_total = lsm_total;
+    return rc;
+}

@@ -192,6 +192,24 @@ class Engine:
                                                   poly_order, C.byref(px)))
         return px.value
 
+    def price_surface_rbergomi_lsm(self, model: dict, strikes, maturities, n_paths: int, r: float, is_call: bool = False,
+                                   poly_order: int = 3, carry: int = capi.MCP_F32, steps_per_year: int = 252, seed: int = 0,
+                                   path_offset: int = 0, mat_first: int = 0, mat_stride: int = 1):
+        """Strike x maturity surface (BASELINE config 5).  Returns (prices[n_mat][n_strikes], std_errors, gen_ms, lsm_ms);
+        entries of maturities this call does not own (mat_first / mat_stride) are NaN."""
+        m = RbergomiParams(model["S0"], model["r"], model["xi"], model["H"], model["eta"], model["rho"], model["dt"])
+        q = LsmParams(r, 0.0, 0.0, model["dt"], int(bool(is_call)), poly_order, capi.MCP_BASIS_MONOMIAL, carry)
+        ks = np.ascontiguousarray(strikes, dtype=np.float64)
+        ts = np.ascontiguousarray(maturities, dtype=np.float64)
+        px = np.full((ts.size, ks.size), np.nan)
+        se = np.full((ts.size, ks.size), np.nan)
+        g, l = C.c_float(), C.c_float()
+        self._chk(self._L.mcp_price_surface_rbergomi_lsm(
+            self._h, C.byref(m), C.byref(q), ks.ctypes.data_as(capi._dp), ks.size, ts.ctypes.data_as(capi._dp), ts.size,
+            steps_per_year, n_paths, seed, path_offset, mat_first, mat_stride, px.ctypes.data_as(capi._dp),
+            se.ctypes.data_as(capi._dp), C.byref(g), C.byref(l)))
+        return px, se, g.value, l.value
+
     # -- the other three plugins (SURVEY 8f) ------------------------------------------------------
     def asymptotic_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, sigma, dividend) -> float:
         px = C.c_double()

@@ -1,0 +1,47 @@
+"""BASELINE config 5 (strike x maturity surface under rough-vol LSM), at sizes the CPU oracle finishes in seconds, plus
+the size-independent properties the domain offers on a larger grid (put prices increase with strike; the rank split
+by maturity reproduces the unsplit surface entry for entry)."""
+import numpy as np
+import pytest
+
+import montecarlooptionspricer_b200 as m
+from conftest import CFG2
+
+pytestmark = pytest.mark.gpu
+MODEL = dict(S0=100.0, r=0.05, xi=0.04, H=0.1, eta=1.9, rho=-0.9, dt=1.0 / 252.0)
+
+
+def test_surface_entries_match_the_oracle(engine, port):
+    strikes, mats = [90.0, 100.0, 110.0], [21 / 252.0, 0.25]
+    n_paths, seed = 6000, 17
+    px, se, _, _ = engine.price_surface_rbergomi_lsm(MODEL, strikes, mats, n_paths, r=0.05, poly_order=3, carry=m.MCP_F64, seed=seed)
+    assert px.shape == (2, 3) and np.all(np.isfinite(px)) and np.all(se >= 0)
+    for mi, T in enumerate(mats):
+        n = int(np.floor(T * 252))
+        # the slab of maturity mi: same generator call the surface routine makes (seed derivation is part of the ABI contract)
+        ps = engine.pathset(n_paths, n)
+        engine.gen_rbergomi(ps, **{k: MODEL[k] for k in ("S0", "r", "xi", "H", "eta", "rho", "dt")},
+                            seed=(seed + 0x9E3779B97F4A7C15 * (mi + 1)) % (1 << 64))
+        slab = ps.download_timemajor()
+        ps.close()
+        for ki, K in enumerate(strikes):
+            want = port.lsm_timemajor_f32(slab, 0.05, K, T, MODEL["dt"], False, 3)
+            assert px[mi, ki] == pytest.approx(want["price"], rel=1e-9, abs=1e-9), (mi, ki)  # parity bar: 1e-9 of max(1, price)
+            assert se[mi, ki] == pytest.approx(want["stderr"], rel=1e-6, abs=1e-9)  # K = 110: in the money at j = 0, V0 is one constant
+
+
+def test_surface_monotone_in_strike_and_rank_split_is_exact(engine):
+    strikes = np.arange(70.0, 131.0, 4.0)            # config 5: 16 strikes K = 70, 74, ..., 130
+    mats = np.arange(1, 9) / 16.0                     # first 8 of the 16 maturities m / 16 y
+    n_paths = 1 << 16
+    full, se, gen_ms, lsm_ms = engine.price_surface_rbergomi_lsm(MODEL, strikes, mats, n_paths, r=0.05, seed=3)
+    assert np.all(np.diff(full, axis=1) >= 0)         # a put is worth more at a higher strike (same paths per maturity)
+    assert np.all(np.diff(full[-1, 5:]) > 0)          # ... strictly, wherever some path is in the money
+    assert np.all(full[:, -1] >= 130.0 - 100.0 - 1e-6)  # deep ITM: at least intrinsic value
+    parts = [engine.price_surface_rbergomi_lsm(MODEL, strikes, mats, n_paths, r=0.05, seed=3, mat_first=g, mat_stride=4)[0] for g in range(4)]
+    merged = np.full_like(full, np.nan)
+    for g, p in enumerate(parts):
+        own = np.arange(len(mats)) % 4 == g
+        assert np.all(np.isnan(p[~own])) and not np.any(np.isnan(p[own]))
+        merged[own] = p[own]
+    np.testing.assert_array_equal(merged, full)       # zero-collective split: bit-identical to the single-rank surface
