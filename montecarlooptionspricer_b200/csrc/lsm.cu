@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -73,6 +74,7 @@ struct SweepArgs {
     int pin_mode;       // 1: evict_last hints, 2: plain accesses under a persisting access-policy window
     McpXchg x;          // peer-memory mailboxes (multi-GPU): the moment all-reduce happens inside this kernel
     unsigned long long seq;  // sequence number of this launch's exchange
+    int l2_resident;    // two slab rows + the carry fit in L2: keep them there instead of streaming
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
@@ -364,9 +366,13 @@ struct FastConsts {
 // Arithmetic of one group of 8 paths held in registers: s8 = S_j, p8 = S_{j-1}, v8 = carry (updated in place).
 // Path e of the group is global path idx[e >> 2] + (e & 3), i.e. two runs of four consecutive paths (the direct-load
 // kernel uses one run of eight: idx1 = idx0 + 4).  TAIL: the ragged last group, paths >= a.n are masked out.
-template <int P, bool TAU, bool TAIL>
+// KIND 0: the common launch (regress-and-decide step that also accumulates the next regression, 251 of 253 launches
+// at config 3) with every mode test resolved at compile time; KIND 1: any launch, flags read at run time.
+template <int P, bool TAU, bool TAIL, int KIND = 1>
 __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastConsts<P>& k, const F8& s8, const F8& p8, F8& v8, int64_t idx0, int64_t idx1,
-                                              int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+                                              int mode_rt, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+    const int mode = KIND == 0 ? 0 : mode_rt;
+    const bool do_moments = KIND == 0 ? true : (a.do_moments != 0), do_final = KIND == 0 ? false : (a.do_final != 0);
     const float2(&s)[4] = s8.q;
     const float2(&sp)[4] = p8.q;
     float2(&v)[4] = v8.q;
@@ -400,11 +406,11 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
             }
         }
     }
-    if (a.do_moments) {
+    if (do_moments) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float2 pp = __fadd2_rn(__ffma2_rn(sp[q], k.sg, k.nsK), k.nsKlo);  // payoff of step j-1 (sign test only)
-            float2 m = make_float2(pp.x > 1e-14f ? 1.f : 0.f, pp.y > 1e-14f ? 1.f : 0.f);  // LSMPricer.cpp:51-58
+            float2 m = make_float2(pp.x > 1e-14f ? 1.f : 0.f, pp.y > 1e-14f ? 1.f : 0.f);  // LSMPricer.cpp:51-58 (one FSET each)
             if (TAIL) {
                 if (!ok[2 * q]) m.x = 0.f;
                 if (!ok[2 * q + 1]) m.y = 0.f;
@@ -422,7 +428,7 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
             }
         }
     }
-    if (a.do_final) {
+    if (do_final) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float2 w = v[q];
@@ -549,6 +555,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void stg4_keep(float* p, float2 a, float2 b) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
 __device__ __forceinline__ void stg4_stream(float* p, float2 a, float2 b) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
@@ -565,13 +579,48 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
     const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
     float* __restrict__ V = reinterpret_cast<float*>(a.V);
-    const int mode = a.terminal ? 2 : a.d.kind[a.j];
     const int tid = threadIdx.x;
 
+    // Programmatic dependent launch: this grid may start while the previous sweep is still in its epilogue.  Everything
+    // up to griddepcontrol.wait touches only what the previous sweep never writes (the path slab, our own shared
+    // memory): the barriers are set up and the S_j / S_{j-1} parts of the first ring stages are already in flight
+    // when the wait returns; the carry tiles and the regression coefficients are fetched after it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int64_t ntile = (a.n + TMA_TILE - 1) / TMA_TILE;
+    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    // streamed tiles leave L2 first -- unless the whole working set (two slab rows + the carry) fits in L2, where the
+    // next sweep finds S_{j-1} (as its S_j) and the carry still resident (multi-GPU shards of config 3)
+    const uint64_t pol = a.l2_resident ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const bool want_v = !a.terminal;  // mode != 2
+    // tile `it` of this CTA, in serpentine order (what the previous sweep touched last is read first)
+    auto tile_of = [&](int64_t it) -> int64_t {
+        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
+        return (a.j & 1) ? (ntile - 1 - t) : t;
+    };
+    // one elected thread: arm the stage's barrier with the bytes of all its copies, start the slab copies (part 1) and
+    // the carry copy (part 2)
+    auto issue = [&](int64_t it, bool part_s, bool part_v) {
+        const int st = (int)(it % n_stages);
+        const int64_t i0 = tile_of(it) * TMA_TILE;
+        const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;  // rows are padded to ld (multiple of 128)
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        float* dst = ring + (size_t)st * (3 * TMA_TILE);
+        if (part_s) {
+            mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (want_v ? 1u : 0u)));
+            bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
+            if (a.do_moments) bulk_g2s(dst + TMA_TILE, Sp + i0, bytes, full + st);
+        }
+        if (part_v && want_v) bulk_g2s_hint(dst + 2 * TMA_TILE, V + i0, bytes, full + st, pol);
+    };
     if (tid == 0) {
         for (int st = 0; st < n_stages; ++st) mbar_init(full + st, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, true, false);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous sweep (carry, coefficients, ticket) is complete and visible
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];
+    if (tid == 0)
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, false, true);
     FastConsts<P> k;
     fast2_load_consts<P>(a, k);
     float2 la[NV];
@@ -579,29 +628,10 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * TMA_NT + tid] = 0.0; }
     __syncthreads();
 
-    const int64_t ntile = (a.n + TMA_TILE - 1) / TMA_TILE;
-    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const uint64_t pol = l2_policy_evict_first();
-    // tile `it` of this CTA, in serpentine order (what the previous sweep touched last is read first)
-    auto tile_of = [&](int64_t it) -> int64_t {
-        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
-        return (a.j & 1) ? (ntile - 1 - t) : t;
-    };
-    auto issue = [&](int64_t it) {  // one elected thread: arm the stage's barrier and start its bulk copies
-        const int st = (int)(it % n_stages);
-        const int64_t i0 = tile_of(it) * TMA_TILE;
-        const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;  // rows are padded to ld (multiple of 128)
-        const uint32_t bytes = (uint32_t)cnt * 4u;
-        float* dst = ring + (size_t)st * (3 * TMA_TILE);
-        mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (mode != 2 ? 1u : 0u)));
-        bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
-        if (a.do_moments) bulk_g2s(dst + TMA_TILE, Sp + i0, bytes, full + st);
-        if (mode != 2) bulk_g2s_hint(dst + 2 * TMA_TILE, V + i0, bytes, full + st, pol);
-    };
-    if (tid == 0)
-        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it);
-
     int since = 0;
+    auto run_tiles = [&](auto kind_tag) {
+    constexpr int KIND = decltype(kind_tag)::value;
+    const bool dm = KIND == 0 ? true : (a.do_moments != 0), wv = KIND == 0 ? true : (mode != 2);
     for (int64_t it = 0; it < my_tiles; ++it) {
         const int st = (int)(it % n_stages);
         const uint32_t parity = (uint32_t)((it / n_stages) & 1);
@@ -613,22 +643,27 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
             s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
         }
         p8 = s8; v8 = s8;
-        if (a.do_moments) {
+        if (dm) {
             const float4 x0 = *reinterpret_cast<const float4*>(buf + TMA_TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + TMA_TILE + 2048 + 4 * tid);
             p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
         }
-        if (mode != 2) {
+        if (wv) {
             const float4 x0 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 2048 + 4 * tid);
             v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
         }
         __syncthreads();  // every thread holds its part of the stage in registers: the slot can be refilled
-        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages);
+        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages, true, true);
 
         const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = i0 + 2048 + 4 * tid;
-        if (i0 + TMA_TILE <= a.n) fast2_compute<P, TAU, false>(a, k, s8, p8, v8, ia, ib, mode, la);
-        else fast2_compute<P, TAU, true>(a, k, s8, p8, v8, ia, ib, mode, la);
-        if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
-        if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+        if (i0 + TMA_TILE <= a.n) fast2_compute<P, TAU, false, KIND>(a, k, s8, p8, v8, ia, ib, mode, la);
+        else fast2_compute<P, TAU, true, KIND>(a, k, s8, p8, v8, ia, ib, mode, la);
+        if (a.l2_resident) {
+            if (ia < a.ld) stg4_keep(V + ia, v8.q[0], v8.q[1]);
+            if (ib < a.ld) stg4_keep(V + ib, v8.q[2], v8.q[3]);
+        } else {
+            if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
+            if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+        }
         if (++since == FLUSH) {
 #pragma unroll
             for (int m = 0; m < NV; ++m) {
@@ -638,6 +673,9 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
             since = 0;
         }
     }
+    };
+    if (mode == 0 && a.do_moments && !a.do_final) run_tiles(std::integral_constant<int, 0>{});
+    else run_tiles(std::integral_constant<int, 1>{});
     if (a.do_moments || a.do_final) {
         double acc[NV];
 #pragma unroll
@@ -959,6 +997,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     const int64_t grid_aux = grid;  // the small streaming kernels keep the occupancy-sized grid
     // TMA-ring kernel (one persistent 512-thread CTA per SM) once there are enough 4096-path tiles to feed every SM
     SweepFn2 sweep_tma = nullptr;
+    const bool tma_pdl = env_int("MCP_SWEEP_PDL", 1) != 0;
     int tma_stages = 0;
     size_t tma_smem = 0;
     const int64_t ntile = (N + TMA_TILE - 1) / TMA_TILE;
@@ -1030,6 +1069,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     a.solve_here = (!multi || p2p) ? 1 : 0;
     a.pin_paths = ((int64_t)env_int("MCP_SWEEP_PIN_MB", 0) << 20) / 4 / 8 * 8;  // carry bytes kept L2-resident
     a.pin_mode = env_int("MCP_SWEEP_PIN_MODE", 1);
+    a.l2_resident = ((size_t)N * 12 <= ((size_t)env_int("MCP_L2_RESIDENT_MB", 104) << 20)) ? 1 : 0;
     if (a.pin_paths > N) a.pin_paths = N / 8 * 8;
     bool window_set = false;
     if (a.pin_paths > 0 && a.pin_mode == 2 && prm->carry == MCP_F32) {
@@ -1061,8 +1101,22 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         a.do_final = (j == 0);
         if (p2p && (a.do_moments || a.do_final)) a.seq = ++ctx->xchg_seq;
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j), st);
-        if (sweep_tma) sweep_tma<<<(unsigned)grid, TMA_NT, tma_smem, st>>>(a, tma_stages);
-        else sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
+        if (sweep_tma) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(TMA_NT);
+            cfg.dynamicSmemBytes = tma_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = tma_pdl ? 1 : 0;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            MCP_CUDA(ctx, cudaLaunchKernelEx(&cfg, sweep_tma, a, tma_stages));
+        } else {
+            sweep<<<(unsigned)grid, LSM_NT, 0, st>>>(a);
+        }
         MCP_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j + 1), st);
         if (a.do_moments && !a.solve_here) {  // multi-GPU: global moments, then every rank solves the same system
