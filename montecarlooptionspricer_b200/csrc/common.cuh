@@ -10,8 +10,9 @@
 
 struct McpNccl;  // dlopen'ed NCCL entry points (ctx.cu)
 
-// Mailbox layout: [parity 0|1][source rank][MCP_XROW doubles]; doubles 0..30 carry data, slot 31 the sequence flag.
-constexpr int MCP_XROW = 32;
+// Mailbox layout: [parity 0|1][source rank][MCP_XROW 8-byte words]; word 2k / 2k+1 = {low / high 32 bits of value k,
+// 32-bit sequence tag}: payload and tag travel in ONE 8-byte store (atomic over NVLink), so no fence and no separate flag.
+constexpr int MCP_XROW = 64;
 constexpr int MCP_XMAX_RANKS = 16;
 struct McpXchg {
     int nranks = 1, rank = 0;

@@ -93,7 +93,7 @@ static void xchg_setup(mcp_ctx* ctx) {
     if (impl && strcmp(impl, "nccl") == 0) return;
     const int n = ctx->nranks;
     if (n < 2 || n > MCP_XMAX_RANKS || !g_nccl.AllGather) return;
-    const size_t box_bytes = (size_t)2 * n * MCP_XROW * sizeof(double);
+    const size_t box_bytes = (size_t)2 * n * MCP_XROW * sizeof(unsigned long long);
     XchgCard mine;
     memset(&mine, 0, sizeof(mine));
     mine.pid = (long long)getpid();

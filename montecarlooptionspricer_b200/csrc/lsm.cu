@@ -707,19 +707,13 @@ __global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* 
 }
 
 // All-reduce (sum) of `vals[0..NV)` across GPUs through the peer-memory mailboxes, executed by ONE CTA per rank (the
-// last one of its sweep launch).  One-shot all-gather: every rank stores its row into the mailbox of every rank
-// over NVLink (plain P2P stores), publishes a sequence flag with release semantics, waits until all rows of its own
-// mailbox carry that sequence, and adds them up IN RANK ORDER -- so every rank obtains the bitwise identical sum and
-// then solves the identical system.  Two mailbox halves (sequence parity) keep exchange s+1 from overwriting rows a
-// slow rank is still reading for exchange s.  A wait that exceeds ~20 s raises the error flag instead of hanging.
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+// last one of its sweep launch).  One-shot all-gather in the style of NCCL's LL protocol: every 8-byte word carries
+// 32 bits of payload and a 32-bit sequence tag, so one plain P2P store per word both delivers and publishes it --
+// one NVLink traversal, no fence, no flag round trip.  Every rank stores its words into the mailbox of every rank,
+// polls its own mailbox until all words carry this exchange's tag, and adds the rows IN RANK ORDER: all ranks obtain
+// the bitwise identical sum and then solve the identical system.  Two mailbox halves (sequence parity) keep
+// exchange s+1 from overwriting words a slow rank is still reading for exchange s.  A poll that exceeds ~20 s raises
+// the error flag instead of hanging.
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -728,29 +722,34 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 template <int NV, int NT>
 __device__ __forceinline__ void xchg_allreduce(const McpXchg& x, unsigned long long seq, double* vals /* shared [NV] */) {
-    static_assert(NV < MCP_XROW, "row too long for the mailbox");
+    static_assert(2 * NV <= MCP_XROW, "row too long for the mailbox");
+    __shared__ unsigned int got[MCP_XMAX_RANKS][2 * NV];
     const int tid = threadIdx.x, n = x.nranks;
     const size_t half = (size_t)(seq & 1ull) * (size_t)n;
-    for (int idx = tid; idx < n * NV; idx += NT) {
-        const int r = idx / NV, k = idx - r * NV;
-        volatile double* row = x.peer[r] + (half + (size_t)x.rank) * MCP_XROW;
-        row[k] = vals[k];
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    for (int idx = tid; idx < n * 2 * NV; idx += NT) {
+        const int r = idx / (2 * NV), w = idx - r * (2 * NV);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w >> 1]);
+        const unsigned long long word = ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
+        volatile unsigned long long* row = reinterpret_cast<volatile unsigned long long*>(x.peer[r]) + (half + (size_t)x.rank) * MCP_XROW;
+        row[w] = word;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < n) {
-        st_release_sys(reinterpret_cast<unsigned long long*>(x.peer[tid] + (half + (size_t)x.rank) * MCP_XROW + (MCP_XROW - 1)), seq);
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(x.peer[x.rank] + (half + (size_t)tid) * MCP_XROW + (MCP_XROW - 1));
+    for (int idx = tid; idx < n * 2 * NV; idx += NT) {
+        const int r = idx / (2 * NV), w = idx - r * (2 * NV);
+        const volatile unsigned long long* row = reinterpret_cast<const volatile unsigned long long*>(x.peer[x.rank]) + (half + (size_t)r) * MCP_XROW;
         const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(flag) < seq) {
+        unsigned long long word = row[w];
+        while ((word & 0xffffffff00000000ull) != tag) {
             if (global_ns() - t0 > 20000000000ull) { *x.err = 1; break; }
+            word = row[w];
         }
+        got[r][w] = (unsigned int)word;
     }
     __syncthreads();
     if (tid < NV) {
-        const volatile double* mine = x.peer[x.rank] + half * MCP_XROW;
         double s = 0.0;
-        for (int r = 0; r < n; ++r) s += mine[(size_t)r * MCP_XROW + tid];
+        for (int r = 0; r < n; ++r)
+            s += __longlong_as_double((long long)(((unsigned long long)got[r][2 * tid + 1] << 32) | (unsigned long long)got[r][2 * tid]));
         vals[tid] = s;
     }
     __syncthreads();
@@ -1004,7 +1003,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     if (ps->dtype == MCP_F32 && prm->carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
         const size_t fixed = 128 + (size_t)nv * TMA_NT * 8;
-        tma_stages = (int)((227u * 1024u - 8192u - fixed) / TMA_STAGE_BYTES);  // 8 KB: the kernel's static shared memory
+        tma_stages = (int)((227u * 1024u - 12288u - fixed) / TMA_STAGE_BYTES);  // 12 KB: the kernel's static shared memory
         const int want = env_int("MCP_SWEEP_STAGES", 0);
         if (want > 0 && want < tma_stages) tma_stages = want;
         if (tma_stages >= 2) {
