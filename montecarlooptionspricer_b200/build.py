@@ -20,6 +20,7 @@ HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "libmcp_b200.so")
 PLUGINS = os.path.join(PKG, "libmcp_b200_plugins.so")
 DEMO = os.path.join(HOST, "plugin_rows_demo")
+LATENCY = os.path.join(HOST, "plugin_latency")
 
 CU_SOURCES = ["ctx.cu", "pathset.cu", "gen_rbergomi.cu", "gen_gbm.cu", "lsm.cu", "pricers.cu", "estimators.cu", "surface.cu"]
 NVCC_FLAGS = [
@@ -72,6 +73,10 @@ def build_plugins(force: bool = False) -> str:
     if os.path.exists(demo_src) and (force or not _newer(DEMO, [demo_src, PLUGINS])):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wall", *inc, demo_src, "-o", DEMO, "-L", PKG, "-lmcp_b200_plugins",
                         "-lmcp_b200", "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
+    lat_src = os.path.join(HOST, "plugin_latency.cpp")
+    if os.path.exists(lat_src) and (force or not _newer(LATENCY, [lat_src, PLUGINS])):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", *inc, lat_src, "-o", LATENCY, "-L", PKG, "-lmcp_b200_plugins", "-lmcp_b200",
+                        "-Wl,-rpath,$ORIGIN/.."], check=True, env=env)
     return PLUGINS
 
 

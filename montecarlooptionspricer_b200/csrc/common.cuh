@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mcp_b200.h"
@@ -52,6 +53,11 @@ struct mcp_ctx {
     // grow-only LSM carry buffer (kept across calls so repeated pricing does not re-allocate)
     void* carry = nullptr;
     size_t carry_bytes = 0;
+    // small-slab pool: device blocks of destroyed pathsets (<= 256 MiB each) are kept for the next mcp_pathset_create on
+    // this ctx -- the reference's row loop creates and drops one path matrix per row (PredictionGen.cpp:736-737), and
+    // cudaMalloc / cudaFree serialise every host thread of the process
+    std::vector<std::pair<void*, size_t>> slab_pool;
+    size_t slab_pool_bytes = 0;
     // cached pathset for mcp_price_rbergomi_lsm
     mcp_pathset* cached_ps = nullptr;
     // optional per-kernel timing
@@ -68,6 +74,7 @@ struct mcp_pathset {
     int dtype = MCP_F32;
     void* data = nullptr;
     size_t bytes = 0;
+    size_t capacity = 0;  // size of the device block behind `data` (>= bytes when it came from the pool)
 };
 
 int mcp_fail(mcp_ctx* ctx, int code, const char* fmt, ...);

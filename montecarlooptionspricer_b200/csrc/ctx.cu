@@ -194,6 +194,8 @@ int mcp_destroy(mcp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->cached_ps) mcp_pathset_destroy(ctx->cached_ps);
+    for (auto& blk : ctx->slab_pool) cudaFree(blk.first);
+    ctx->slab_pool.clear();
     xchg_teardown(ctx);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -211,6 +213,7 @@ const char* mcp_last_error(const mcp_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int mcp_set_stream(mcp_ctx* ctx, void* s) {
     if (!ctx) return MCP_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);  // pooled slabs and workspaces are recycled in stream order
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return MCP_OK;
 }

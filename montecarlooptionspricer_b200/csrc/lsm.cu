@@ -869,6 +869,125 @@ __global__ void lsm_fill_tau_kernel(int32_t* __restrict__ tau, int64_t n, int32_
     if (i < n) tau[i] = val;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Whole backward induction in ONE launch for small path sets (the reference's production rows are 250 paths,
+// PredictionGen.cpp:719): a single CTA keeps the fp64 carry in shared memory and loops over the time steps with
+// block barriers -- regression moments, fold, solve and decision of every step without leaving the kernel.  Same
+// arithmetic as the parity kernel (all decisions in fp64 on the stored values).  One launch instead of one per time
+// step matters twice for the row loop of the reference: per-row latency, and the launch stream of 16 host threads no
+// longer serialises on the driver.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMALL_NT = 512;
+constexpr int SMALL_MAX_PATHS = 4096;
+
+template <int NV>
+__device__ __forceinline__ void small_block_sum(double (&acc)[NV], double* __restrict__ out /* shared [NV] */) {
+    __shared__ double red[SMALL_NT / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < SMALL_NT / 32; ++w) s += red[w][threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+template <typename ST, int P>
+__global__ void __launch_bounds__(SMALL_NT, 1) lsm_small_kernel(SweepArgs a, int M) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    extern __shared__ double sV[];  // carry [n]
+    __shared__ double mom[NV], cf[COEF_LD], fin_s[2];
+    const ST* __restrict__ S = reinterpret_cast<const ST*>(a.S);
+    const int n = (int)a.n, tid = threadIdx.x;
+    auto ldS = [&](int j, int i) -> double { return (double)S[(int64_t)j * a.ld + i]; };
+
+    for (int i = tid; i < n; i += SMALL_NT) sV[i] = payoff_fn(a.is_call, ldS(M - 1, i), a.K);  // LSMPricer.cpp:37-40
+    __syncthreads();
+    for (int j = M - 2; j >= 0; --j) {                                                          // :42
+        if (a.d.kind[j] == STEP_DISCOUNT) {                                                     // :43-49
+            for (int i = tid; i < n; i += SMALL_NT) sV[i] *= a.disc;
+            __syncthreads();
+            continue;
+        }
+        const double mu = a.d.mu[j], inv_s = a.d.inv_s[j];
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (int i = tid; i < n; i += SMALL_NT) {
+            const double s = ldS(j, i);
+            if (payoff_fn(a.is_call, s, a.K) > 1e-14) {                                         // :51-58
+                const double x = (s - mu) * inv_s, y = sV[i] * a.disc;                          // :69
+                double xp = x;
+                acc[0] += 1.0;
+                acc[2 * P + 1] += y;
+#pragma unroll
+                for (int k = 1; k <= 2 * P; ++k) {
+                    acc[k] += xp;
+                    if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
+                    if (k < 2 * P) xp *= x;
+                }
+            }
+        }
+        small_block_sum<NV>(acc, mom);
+        if (tid == 0) {
+            solve_normal_equations<P>(mom, a.d.coef + (int64_t)j * COEF_LD);                    // :76
+            for (int k = 0; k < COEF_LD; ++k) cf[k] = a.d.coef[(int64_t)j * COEF_LD + k];
+        }
+        __syncthreads();
+        double c[P + 1];
+#pragma unroll
+        for (int k = 0; k <= P; ++k) c[k] = cf[k];
+        for (int i = tid; i < n; i += SMALL_NT) {
+            const double s = ldS(j, i), pay = payoff_fn(a.is_call, s, a.K);
+            const double x = (s - mu) * inv_s;
+            double cont = c[P];
+#pragma unroll
+            for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
+            const bool itm = pay > 1e-14, ex = !(pay < cont);                                   // :55, :85
+            const double carried = pay < 1e-14 ? sV[i] * a.disc : 0.0;                          // :89-94; == 1e-14 keeps the initial 0 (:35)
+            sV[i] = itm ? (ex ? pay : cont) : carried;
+            if (a.tau && itm && ex) a.tau[i] = j;
+        }
+        __syncthreads();
+    }
+    // payoff averaging (:97-101) + two-pass standard error
+    double t[2] = {0.0, 0.0};
+    for (int i = tid; i < n; i += SMALL_NT) t[0] += sV[i];
+    small_block_sum<2>(t, fin_s);
+    const double mean = fin_s[0] / (double)n;
+    double q[2] = {0.0, 0.0};
+    for (int i = tid; i < n; i += SMALL_NT) {
+        const double dlt = sV[i] - mean;
+        q[0] = fma(dlt, dlt, q[0]);
+        reinterpret_cast<double*>(a.V)[i] = sV[i];
+    }
+    __shared__ double fin_q[2];
+    small_block_sum<2>(q, fin_q);
+    if (tid == 0) { a.d.fin[0] = fin_s[0]; a.d.fin[1] = fin_q[0]; a.d.fin[2] = (double)n; }
+}
+
+typedef void (*SmallFn)(SweepArgs, int);
+template <typename ST>
+SmallFn pick_small(int p) {
+    switch (p) {
+        case 0: return lsm_small_kernel<ST, 0>;
+        case 1: return lsm_small_kernel<ST, 1>;
+        case 2: return lsm_small_kernel<ST, 2>;
+        case 3: return lsm_small_kernel<ST, 3>;
+        case 4: return lsm_small_kernel<ST, 4>;
+        case 5: return lsm_small_kernel<ST, 5>;
+        default: return lsm_small_kernel<ST, 6>;
+    }
+}
+
 typedef void (*SweepFn)(SweepArgs);
 typedef void (*SweepFn2)(SweepArgs, int);
 
@@ -983,10 +1102,13 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
 
     const int M = ps->n_steps + 1;
     const int64_t N = ps->n_paths;
-    const size_t csz = prm->carry == MCP_F32 ? 4 : 8;
+    // small path sets: the whole induction in one single-CTA launch (always with the fp64 carry)
+    const bool small = N <= SMALL_MAX_PATHS && !(ctx->nranks > 1 && ctx->comm) && env_int("MCP_LSM_SMALL", 1) != 0;
+    const int carry = small ? (int)MCP_F64 : prm->carry;
+    const size_t csz = carry == MCP_F32 ? 4 : 8;
     const uint64_t launches0 = ctx->launches;
 
-    SweepFn sweep = pick_sweep(ps->dtype, prm->carry, p, first_exercise != nullptr);
+    SweepFn sweep = pick_sweep(ps->dtype, carry, p, first_exercise != nullptr);
     int occ = 0;
     MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep, LSM_NT, 0));
     if (occ < 1) occ = 1;
@@ -1000,7 +1122,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     int tma_stages = 0;
     size_t tma_smem = 0;
     const int64_t ntile = (N + TMA_TILE - 1) / TMA_TILE;
-    if (ps->dtype == MCP_F32 && prm->carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
+    if (ps->dtype == MCP_F32 && carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
         const size_t fixed = 128 + (size_t)nv * TMA_NT * 8;
         tma_stages = (int)((227u * 1024u - 12288u - fixed) / TMA_STAGE_BYTES);  // 12 KB: the kernel's static shared memory
@@ -1093,7 +1215,16 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         cudaGetLastError();
     }
     const int nm = 3 * p + 2;
-    for (int j = M - 1; j >= 0; --j) {
+    if (small) {
+        SmallFn fn = ps->dtype == MCP_F32 ? pick_small<float>(p) : pick_small<double>(p);
+        const size_t smem = (size_t)N * sizeof(double);
+        if (smem > 40 * 1024) MCP_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 0), st);
+        fn<<<1, SMALL_NT, smem, st>>>(a, M);
+        MCP_LAUNCH_CHECK(ctx);
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 1), st);
+    }
+    for (int j = M - 1; j >= 0 && !small; --j) {
         a.j = j;
         a.terminal = (j == M - 1);
         a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
@@ -1132,19 +1263,21 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     }
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
-    const double nloc = (double)N;
-    if (!p2p) MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
-    if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
-    if (prm->carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
-    else lsm_sqdev_kernel<double><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
-    MCP_LAUNCH_CHECK(ctx);
-    lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid_aux, 1, d.fin + 1);
-    MCP_LAUNCH_CHECK(ctx);
-    MCP_TRY(mcp_allreduce_f64(ctx, d.fin + 1, 1));
+    if (!small) {
+        const double nloc = (double)N;
+        if (!p2p) MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
+        if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
+        if (carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
+        else lsm_sqdev_kernel<double><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
+        MCP_LAUNCH_CHECK(ctx);
+        lsm_reduce_kernel<<<1, 256, 0, st>>>(d.partial, (int)grid_aux, 1, d.fin + 1);
+        MCP_LAUNCH_CHECK(ctx);
+        MCP_TRY(mcp_allreduce_f64(ctx, d.fin + 1, 1));
+    }  // the single-launch kernel leaves {sum V0, sum (V0 - mean)^2, N} itself
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     MCP_CUDA(ctx, cudaMemcpyAsync(fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
     if (dV0) {
-        if (prm->carry == MCP_F32) lsm_copy_v0_kernel<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)dV, N, dV0);
+        if (carry == MCP_F32) lsm_copy_v0_kernel<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)dV, N, dV0);
         else lsm_copy_v0_kernel<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const double*)dV, N, dV0);
         MCP_LAUNCH_CHECK(ctx);
         MCP_CUDA(ctx, cudaMemcpyAsync(v0, dV0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
@@ -1177,7 +1310,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     ctx->prof.sweep_kernels_ms = 0.f;
     ctx->prof.n_sweep_launches = 0;
     if (ctx->profiling) {
-        for (int j = 0; j < M; ++j) {
+        for (int j = 0; j < (small ? 1 : M); ++j) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, mcp_prof_event(ctx, 2 * (size_t)j), mcp_prof_event(ctx, 2 * (size_t)j + 1)) == cudaSuccess)
                 ctx->prof.sweep_kernels_ms += t;

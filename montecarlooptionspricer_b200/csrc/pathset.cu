@@ -26,6 +26,19 @@ int mcp_pathset_create(mcp_ctx* ctx, int64_t n_paths, int n_steps, int dtype, mc
     ps->ld = mcp_round_up(n_paths, 128);
     ps->dtype = dtype;
     ps->bytes = (size_t)ps->ld * (size_t)(n_steps + 1) * (dtype == MCP_F32 ? 4 : 8);
+    // best fit from the ctx pool (stream order makes reuse safe: every user of the old slab ran on ctx->stream)
+    int best = -1;
+    for (int i = 0; i < (int)ctx->slab_pool.size(); ++i)
+        if (ctx->slab_pool[i].second >= ps->bytes && (best < 0 || ctx->slab_pool[i].second < ctx->slab_pool[best].second)) best = i;
+    if (best >= 0 && ctx->slab_pool[best].second <= 4 * ps->bytes + (1u << 20)) {
+        ps->data = ctx->slab_pool[best].first;
+        ps->capacity = ctx->slab_pool[best].second;
+        ctx->slab_pool_bytes -= ps->capacity;
+        ctx->slab_pool.erase(ctx->slab_pool.begin() + best);
+        *out = ps;
+        return MCP_OK;
+    }
+    ps->capacity = ps->bytes;
     if (cudaMalloc(&ps->data, ps->bytes) != cudaSuccess) {
         cudaGetLastError();
         delete ps;
@@ -38,9 +51,16 @@ int mcp_pathset_create(mcp_ctx* ctx, int64_t n_paths, int n_steps, int dtype, mc
 int mcp_pathset_destroy(mcp_pathset* ps) {
     if (!ps) return MCP_OK;
     cudaSetDevice(ps->ctx->device);
-    cudaStreamSynchronize(ps->ctx->stream);
-    if (ps->ctx->cached_ps == ps) ps->ctx->cached_ps = nullptr;
-    if (ps->data) cudaFree(ps->data);
+    mcp_ctx* ctx = ps->ctx;
+    if (ps->capacity > ((size_t)256 << 20)) cudaStreamSynchronize(ctx->stream);  // pooled blocks are reused in stream order instead
+    if (ctx->cached_ps == ps) ctx->cached_ps = nullptr;
+    constexpr size_t POOL_BLOCK_MAX = (size_t)256 << 20, POOL_TOTAL_MAX = (size_t)1 << 30;
+    if (ps->data && ps->capacity <= POOL_BLOCK_MAX && ctx->slab_pool_bytes + ps->capacity <= POOL_TOTAL_MAX && ctx->slab_pool.size() < 16) {
+        ctx->slab_pool.push_back(std::make_pair(ps->data, ps->capacity));
+        ctx->slab_pool_bytes += ps->capacity;
+    } else if (ps->data) {
+        cudaFree(ps->data);
+    }
     delete ps;
     return MCP_OK;
 }

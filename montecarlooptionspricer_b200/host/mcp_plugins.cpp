@@ -3,6 +3,7 @@
 #include "mcp_plugins.hpp"
 
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <random>
 
@@ -32,13 +33,39 @@ Engine& pick(Engine* e) { return e ? *e : Engine::thread_default(); }
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------- upload cache
+// The reference's row loop hands the SAME path matrix to four pricers in a row (PredictionGen.cpp:788-791).  Each
+// Engine therefore keeps the last uploaded matrix on the device, keyed by its dimensions and a 64-bit hash of its
+// contents: the second to fourth pricer of a row find their slab already resident.  Matrices above 64 MiB are not
+// cached (hashing them would cost as much as the copy).
+namespace {
+
+uint64_t hash_rows(const PathMatrix& paths) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)paths.size() << 32) ^ (uint64_t)paths[0].size();
+    for (const auto& row : paths) {
+        const double* p = row.data();
+        for (size_t j = 0; j < row.size(); ++j) {
+            uint64_t w;
+            std::memcpy(&w, p + j, 8);
+            h = (h ^ w) * 0x100000001B3ull;
+            h ^= h >> 29;
+        }
+    }
+    return h;
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------ Engine
 Engine::Engine(int device) : device_(device) {
     const int rc = mcp_create(device, &ctx_);
     if (rc != MCP_OK) throw std::runtime_error(std::string("mcp_b200: ") + mcp_last_error(nullptr));
 }
 
-Engine::~Engine() { mcp_destroy(ctx_); }
+Engine::~Engine() {
+    if (cache_ps_) mcp_pathset_destroy(cache_ps_);
+    mcp_destroy(ctx_);
+}
 
 Engine& Engine::thread_default() {
     thread_local std::unique_ptr<Engine> eng;
@@ -74,16 +101,34 @@ DevicePaths::DevicePaths(Engine& eng, const PathMatrix& paths, int dtype) {
     bool ragged = false;
     if (!row_pointers(paths, rows, &ragged))
         throw std::runtime_error(ragged ? "mcp_b200: ragged pricePaths (rows of different length)" : "mcp_b200: Empty pricePaths.");
-    eng.check(mcp_pathset_create(eng.handle(), (int64_t)paths.size(), (int)paths[0].size() - 1, dtype, &ps_));
+    const size_t n = paths.size(), m = paths[0].size();
+    const bool cacheable = dtype == MCP_F64 && n * m * sizeof(double) <= ((size_t)64 << 20);
+    uint64_t h = 0;
+    if (cacheable) {
+        h = hash_rows(paths);
+        if (eng.cache_ps_ && eng.cache_n_ == n && eng.cache_m_ == m && eng.cache_hash_ == h) {
+            ps_ = eng.cache_ps_;  // resident already
+            owned_ = false;
+            return;
+        }
+    }
+    eng.check(mcp_pathset_create(eng.handle(), (int64_t)n, (int)m - 1, dtype, &ps_));
     const int rc = mcp_pathset_upload_rows_f64(ps_, rows.data());
     if (rc != MCP_OK) {
         mcp_pathset_destroy(ps_);
         ps_ = nullptr;
         eng.check(rc);
     }
+    if (cacheable) {
+        if (eng.cache_ps_) mcp_pathset_destroy(eng.cache_ps_);
+        eng.cache_ps_ = ps_; eng.cache_n_ = n; eng.cache_m_ = m; eng.cache_hash_ = h;
+        owned_ = false;  // the engine's cache owns it now
+    }
 }
 
-DevicePaths::~DevicePaths() { mcp_pathset_destroy(ps_); }
+DevicePaths::~DevicePaths() {
+    if (owned_) mcp_pathset_destroy(ps_);
+}
 
 // ------------------------------------------------------------------------------------------ RoughVolatility
 RoughVolatility::RoughVolatility() : seed_(entropy_seed()) {}
@@ -128,17 +173,15 @@ PathMatrix RoughVolatility::GenerateWithParams(const mcp_rbergomi_params& prm, i
 
 // ------------------------------------------------------------------------------------------------- LSM
 double LSM::PredictOptionPrice(const PathMatrix& paths, double r, double strike, double maturity, double dt, bool isCall, int polyOrder) {
-    std::vector<const double*> rows;
-    bool ragged = false;
-    if (!row_pointers(paths, rows, &ragged)) {
-        if (ragged) throw std::runtime_error("mcp_b200: ragged pricePaths (rows of different length)");
-        throw std::runtime_error("LSM::PredictOptionPrice: Empty pricePaths.");  // LSMPricer.cpp:28-30
-    }
+    if (paths.empty() || paths[0].empty()) throw std::runtime_error("LSM::PredictOptionPrice: Empty pricePaths.");  // LSMPricer.cpp:28-30
     Engine& eng = pick(engine_);
-    double price = 0.0;
-    eng.check(mcp_lsm_price_host_rows(eng.handle(), rows.data(), (int64_t)paths.size(), (int)paths[0].size(), r, strike, maturity, dt,
-                                      isCall ? 1 : 0, polyOrder, &price));
-    return price;
+    DevicePaths dp(eng, paths);  // fp64 slab: every decision on the caller's doubles
+    mcp_lsm_params prm;
+    prm.r = r; prm.strike = strike; prm.maturity = maturity; prm.dt = dt;
+    prm.is_call = isCall ? 1 : 0; prm.poly_order = polyOrder; prm.basis = MCP_BASIS_MONOMIAL; prm.carry = MCP_F64;
+    mcp_lsm_result res;
+    eng.check(mcp_lsm_price(eng.handle(), dp.handle(), &prm, &res, nullptr, nullptr, nullptr));
+    return res.price;
 }
 
 // ---------------------------------------------------------------------------------- MartingaleOptimization

@@ -45,11 +45,17 @@ public:
     void check(int status) const;
 
 private:
+    friend class DevicePaths;
     mcp_ctx* ctx_ = nullptr;
     int device_ = 0;
+    // last uploaded path matrix (<= 64 MiB), keyed by dimensions + content hash: see DevicePaths
+    mcp_pathset* cache_ps_ = nullptr;
+    size_t cache_n_ = 0, cache_m_ = 0;
+    uint64_t cache_hash_ = 0;
 };
 
-// Device-resident copy of a caller's path matrix (fp64 slab, time-major); destroyed with the object.
+// Device-resident copy of a caller's path matrix (fp64 slab, time-major).  Matrices up to 64 MiB are kept in the
+// engine's one-entry cache keyed by a content hash, so consecutive pricers called on the same matrix upload it once.
 class DevicePaths {
 public:
     DevicePaths(Engine& eng, const PathMatrix& paths, int dtype = MCP_F64);
@@ -60,6 +66,7 @@ public:
 
 private:
     mcp_pathset* ps_ = nullptr;
+    bool owned_ = true;  // false when the slab lives in the engine's upload cache
 };
 
 class RoughVolatility {

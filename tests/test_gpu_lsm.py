@@ -209,3 +209,20 @@ def test_lsm_tma_ring_kernel_matches_direct_kernel_and_oracle(engine, port, monk
         agree = np.mean(got["3"].first_exercise == want["first_ex"])
         assert agree > 0.9999, agree  # fp32 decisions differ from the fp64 oracle at near-ties only
     ps.close()
+
+
+@pytest.mark.parametrize("n_paths,n,p,is_call,K", [(250, 62, 2, False, 100.0), (250, 165, 2, True, 98.0), (1, 10, 2, False, 100.0),
+                                                    (4096, 50, 3, False, 100.0), (777, 30, 4, False, 104.0), (3000, 20, 0, False, 101.0)])
+def test_lsm_single_launch_kernel_for_small_path_sets(engine, port, monkeypatch, n_paths, n, p, is_call, K):
+    """Up to 4096 paths (the reference's production rows are 250, PredictionGen.cpp:719) the whole backward induction
+    is ONE launch.  Parity with the oracle as for the per-step kernels, and agreement with them on the same input."""
+    paths = gbm_paths(port, n_paths, n, seed=n_paths + n)
+    got, want = check_parity(engine, port, paths, 0.04, K, 1.0, 1.0 / n, is_call, p)
+    assert got.n_kernel_launches < 12          # scale tables, tau fill, the induction, output copies
+    monkeypatch.setenv("MCP_LSM_SMALL", "0")
+    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+    big = engine.lsm_price(ps, 0.04, K, 1.0, 1.0 / n, is_call, p, carry=m.MCP_F64, want_first_exercise=True)
+    ps.close()
+    assert big.n_kernel_launches > n
+    assert abs(big.price - got.price) <= 1e-10 * max(1.0, abs(got.price))
+    assert np.array_equal(big.first_exercise, got.first_exercise)
