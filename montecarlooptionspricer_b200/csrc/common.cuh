@@ -47,6 +47,10 @@ struct mcp_ctx {
     // grow-only device scratch (regression partials, coefficient tables, transposition staging ...)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // pinned parameter ring (1 MiB): small host->device tables and device->host results go through it, so no copy of
+    // the per-row calls touches pageable memory (pageable copies serialise all host threads inside the driver)
+    unsigned char* stage = nullptr;
+    size_t stage_off = 0;
     // grow-only pinned host staging
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -81,6 +85,12 @@ int mcp_fail(mcp_ctx* ctx, int code, const char* fmt, ...);
 int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes);
 int mcp_pinned_reserve(mcp_ctx* ctx, size_t bytes);
 int mcp_carry_reserve(mcp_ctx* ctx, size_t bytes);
+// pinned scratch of `bytes` from the ctx ring (valid until ~1 MiB more has been handed out); nullptr when too large
+void* mcp_stage_alloc(mcp_ctx* ctx, size_t bytes);
+// host -> device through the pinned ring (falls back to a direct copy for large sources)
+int mcp_h2d(mcp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+// once per (device, kernel, dynamic smem): raise the kernel's dynamic shared-memory limit and query its occupancy
+int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, int* occ_out);
 // all-reduce (sum, fp64) of a device buffer on ctx->stream; no-op without a communicator
 int mcp_allreduce_f64(mcp_ctx* ctx, double* dev, int count);
 // event `i` of the profiling pool (created on demand)

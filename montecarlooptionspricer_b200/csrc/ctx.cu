@@ -7,6 +7,9 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 static thread_local std::string g_create_err;
@@ -159,6 +162,11 @@ int mcp_abi_version(void) { return MCP_B200_ABI_VERSION; }
 int mcp_create(int device, mcp_ctx** out) {
     if (!out) return mcp_fail(nullptr, MCP_ERR_INVALID, "mcp_create: out is NULL");
     *out = nullptr;
+    if (const char* bs = getenv("MCP_SYNC_MODE")) {  // host-thread behaviour while waiting: spin (default) | yield | block
+        const unsigned f = strcmp(bs, "block") == 0 ? cudaDeviceScheduleBlockingSync : strcmp(bs, "yield") == 0 ? cudaDeviceScheduleYield : cudaDeviceScheduleSpin;
+        cudaSetDeviceFlags(f);
+        cudaGetLastError();
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -201,6 +209,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->carry) cudaFree(ctx->carry);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -298,6 +307,77 @@ cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i) {
         ctx->prof_ev.push_back(e);
     }
     return ctx->prof_ev[i];
+}
+
+constexpr size_t MCP_STAGE_BYTES = (size_t)1 << 20;
+
+void* mcp_stage_alloc(mcp_ctx* ctx, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    if (bytes > MCP_STAGE_BYTES / 4) return nullptr;
+    if (!ctx->stage) {
+        void* p = nullptr;
+        if (cudaMallocHost(&p, MCP_STAGE_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->stage = (unsigned char*)p;
+        ctx->stage_off = 0;
+    }
+    if (ctx->stage_off + bytes > MCP_STAGE_BYTES) {  // wrap: everything handed out before must have been consumed
+        cudaStreamSynchronize(ctx->stream);
+        ctx->stage_off = 0;
+    }
+    void* out = ctx->stage + ctx->stage_off;
+    ctx->stage_off += bytes;
+    return out;
+}
+
+int mcp_h2d(mcp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes == 0) return MCP_OK;
+    void* pin = mcp_stage_alloc(ctx, bytes);
+    if (pin) {
+        memcpy(pin, src_host, bytes);
+        MCP_CUDA(ctx, cudaMemcpyAsync(dst_dev, pin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        MCP_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's buffer may go away
+    }
+    return MCP_OK;
+}
+
+namespace {
+struct KernelKey {
+    int device;
+    const void* fn;
+    size_t smem;
+    int block;
+    bool operator<(const KernelKey& o) const {
+        if (device != o.device) return device < o.device;
+        if (fn != o.fn) return fn < o.fn;
+        if (smem != o.smem) return smem < o.smem;
+        return block < o.block;
+    }
+};
+std::mutex g_kernel_mu;
+std::map<KernelKey, int> g_kernel_occ;
+}  // namespace
+
+int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, int* occ_out) {
+    const KernelKey key{ctx->device, kernel, smem, block};
+    {
+        std::lock_guard<std::mutex> lk(g_kernel_mu);
+        auto it = g_kernel_occ.find(key);
+        if (it != g_kernel_occ.end()) {
+            if (occ_out) *occ_out = it->second;
+            return MCP_OK;
+        }
+    }
+    if (smem > 48 * 1024) MCP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
+    {
+        std::lock_guard<std::mutex> lk(g_kernel_mu);
+        g_kernel_occ[key] = occ;
+    }
+    if (occ_out) *occ_out = occ;
+    return MCP_OK;
 }
 
 int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes) {

@@ -538,9 +538,8 @@ int launch_tp(mcp_ctx* ctx, const RbParams& P, const PhiloxKeys& K, const float2
     void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const int*, const float*, float*, float*);
     if (inject) kern = dump ? rbergomi_paths_kernel<TP, true, true> : rbergomi_paths_kernel<TP, true, false>;
     else kern = dump ? rbergomi_paths_kernel<TP, false, true> : rbergomi_paths_kernel<TP, false, false>;
-    MCP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)kern, NT, smem, &occ));
     if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: kernel does not fit (smem %zu)", smem);
     const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
     int64_t grid = (int64_t)ctx->sm_count * occ;
@@ -566,13 +565,19 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, double xi, std::
     for (int i = 0; i <= n; ++i) lam[i] = 0.5 * pow((double)i * dt, 2.0 * H);
     const double scale = sqrt(2.0 * H) * eta / (double)Mp * log2e;
     phis.assign((size_t)2 * Mp, 0.f);
+    std::vector<double> cs((size_t)M), sn((size_t)M);  // e^{+2 pi i q / M}, q < M: every term of the DFT below is one of these
+    for (int q = 0; q < M; ++q) {
+        const double ang = 2.0 * M_PI * (double)q / (double)M;
+        cs[q] = cos(ang);
+        sn[q] = sin(ang);
+    }
     for (int k = 0; k < n; ++k) {
         double re = 0.0, im = 0.0;
+        int idx = 0;  // (k * i) mod M, advanced incrementally (M is a power of two)
         for (int i = 0; i <= n; ++i) {
-            const long idx = ((long)k * i) % M;
-            const double ang = 2.0 * M_PI * (double)idx / (double)M;
-            re += lam[i] * cos(ang);
-            im += lam[i] * sin(ang);
+            re += lam[i] * cs[idx];
+            im += lam[i] * sn[idx];
+            idx = (idx + k) & (M - 1);
         }
         phis[2 * k] = (float)(re * scale);
         phis[2 * k + 1] = (float)(im * scale);
@@ -663,11 +668,14 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     int* d_pos = (int*)(d_comp2 + Mp);
     float* d_slot = (float*)(base + mcp_round_up((int64_t)tab_bytes, 256));  // [4n][pc]  slot-major
     float* d_rows = d_slot + (size_t)4 * n * pc;                             // [pc][4n]  host order
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_phis, phis.data(), (size_t)Mp * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_tw, tw.data(), (size_t)Mp * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_comp2, comp2.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_pos, pos.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    {   // the four tables are contiguous on the device: one copy through the pinned ring
+        std::vector<unsigned char> pack(tab_bytes);
+        memcpy(pack.data(), phis.data(), (size_t)Mp * 8);
+        memcpy(pack.data() + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
+        memcpy(pack.data() + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
+        memcpy(pack.data() + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
+        MCP_TRY(mcp_h2d(ctx, d_phis, pack.data(), tab_bytes));
+    }
 
     const PhiloxKeys K = philox_make_keys(seed);
     int TP = 32;
@@ -690,9 +698,8 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
             void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const float*, float*, float*);
             if (inject) kern = dmp ? rbergomi_paths_n256_kernel<true, true> : rbergomi_paths_n256_kernel<true, false>;
             else kern = dmp ? rbergomi_paths_n256_kernel<false, true> : rbergomi_paths_n256_kernel<false, false>;
-            MCP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, N256_SMEM));
             int occ = 0;
-            MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, N256_SMEM));
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)kern, NT, N256_SMEM, &occ));
             if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n256 kernel does not fit");
             const int64_t n_tiles = (Q.n_paths + 31) / 32;
             int64_t grid = (int64_t)ctx->sm_count * occ;

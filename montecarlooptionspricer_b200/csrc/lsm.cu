@@ -1110,7 +1110,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
 
     SweepFn sweep = pick_sweep(ps->dtype, carry, p, first_exercise != nullptr);
     int occ = 0;
-    MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep, LSM_NT, 0));
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)sweep, LSM_NT, 0, &occ));
     if (occ < 1) occ = 1;
     int64_t grid = (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4);
     const int64_t cap = (int64_t)ctx->sm_count * occ;
@@ -1131,7 +1131,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         if (tma_stages >= 2) {
             sweep_tma = first_exercise ? pick_sweep_tma<true>(p) : pick_sweep_tma<false>(p);
             tma_smem = (size_t)tma_stages * TMA_STAGE_BYTES + fixed;
-            MCP_CUDA(ctx, cudaFuncSetAttribute(sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)sweep_tma, TMA_NT, tma_smem, nullptr));
             grid = ctx->sm_count < ntile ? ctx->sm_count : ntile;
         }
     }
@@ -1162,7 +1162,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
 
     cudaStream_t st = ctx->stream;
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d.kind, kind.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d.kind, kind.data(), (size_t)M * 4));
     MCP_CUDA(ctx, cudaMemsetAsync(d.coef, 0, (size_t)M * COEF_LD * 8, st));
     MCP_CUDA(ctx, cudaMemsetAsync(d.counter, 0, 4, st));
 
@@ -1218,7 +1218,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     if (small) {
         SmallFn fn = ps->dtype == MCP_F32 ? pick_small<float>(p) : pick_small<double>(p);
         const size_t smem = (size_t)N * sizeof(double);
-        if (smem > 40 * 1024) MCP_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, SMALL_NT, (size_t)SMALL_MAX_PATHS * sizeof(double), nullptr));
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 0), st);
         fn<<<1, SMALL_NT, smem, st>>>(a, M);
         MCP_LAUNCH_CHECK(ctx);
@@ -1265,7 +1265,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
     if (!small) {
         const double nloc = (double)N;
-        if (!p2p) MCP_CUDA(ctx, cudaMemcpyAsync(d.fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
+        if (!p2p) MCP_TRY(mcp_h2d(ctx, d.fin + 2, &nloc, 8));
         if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
         if (carry == MCP_F32) lsm_sqdev_kernel<float><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const float*)dV, N, d.fin, d.partial);
         else lsm_sqdev_kernel<double><<<(unsigned)grid_aux, LSM_NT, 0, st>>>((const double*)dV, N, d.fin, d.partial);
@@ -1275,7 +1275,8 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         MCP_TRY(mcp_allreduce_f64(ctx, d.fin + 1, 1));
     }  // the single-launch kernel leaves {sum V0, sum (V0 - mean)^2, N} itself
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    MCP_CUDA(ctx, cudaMemcpyAsync(fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
+    double* fin_pin = (double*)mcp_stage_alloc(ctx, 3 * 8);
+    MCP_CUDA(ctx, cudaMemcpyAsync(fin_pin ? fin_pin : fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
     if (dV0) {
         if (carry == MCP_F32) lsm_copy_v0_kernel<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)dV, N, dV0);
         else lsm_copy_v0_kernel<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const double*)dV, N, dV0);
@@ -1294,6 +1295,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     if (p2p) MCP_CUDA(ctx, cudaMemcpyAsync(&xerr, ctx->xchg.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     MCP_CUDA(ctx, cudaGetLastError());
+    if (fin_pin) memcpy(fin, fin_pin, 3 * 8);
     if (xerr) return mcp_fail(ctx, MCP_ERR_NCCL, "lsm: peer-memory moment exchange timed out (a rank did not reach the same sweep step)");
 
     const double ng = fin[2];

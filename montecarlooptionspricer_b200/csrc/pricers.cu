@@ -9,6 +9,7 @@
 // Per-step scalars (discount factors, exercise boundary, maturity cut) are evaluated on the host in double exactly
 // as the reference writes them and handed to the kernels as tables.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -270,6 +271,81 @@ __global__ void __launch_bounds__(PR_NT) branch_upper_kernel(const ST* __restric
     }
 }
 
+// Both bounds in ONE launch for small path sets (<= 4096 paths: the reference's rows are 250): a single CTA keeps the
+// suffix maxima F and the running best in shared memory and walks the time indices downwards with block barriers
+// (gather from F, barrier, update F).  Same resampling stream and arithmetic as the per-date kernels above.
+constexpr int BR_SMALL_NT = 512;
+constexpr int BR_SMALL_MAX = 4096;
+
+template <typename ST>
+__global__ void __launch_bounds__(BR_SMALL_NT, 1) branch_small_kernel(const ST* __restrict__ S, int64_t ld, int n, int j_hi, int j_lo, int kend, int ex_back,
+                                                                     const int* __restrict__ is_ex, const int* __restrict__ ex, int n_ex,
+                                                                     const double* __restrict__ disc, double K, int is_call, int n_br, PhiloxKeys keys,
+                                                                     uint64_t path_offset, const int32_t* __restrict__ inj, double* __restrict__ out) {
+    extern __shared__ double sm[];  // F[n] | best[n]
+    double* F = sm;
+    double* best = sm + n;
+    __shared__ double red[BR_SMALL_NT / 32][2];
+    const int tid = threadIdx.x;
+    double lower = 0.0;
+    for (int i = tid; i < n; i += BR_SMALL_NT) {
+        F[i] = 0.0;
+        best[i] = 0.0;
+        double b = 0.0;  // lower bound: first listed date with a positive discounted payoff (:55-70)
+        for (int e = 0; e < n_ex; ++e) {
+            const int j = ex[e];
+            const double d = disc[j] * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
+            if (d > b) { b = d; break; }
+        }
+        lower += b;
+    }
+    __syncthreads();
+    for (int j = j_hi; j >= j_lo; --j) {
+        const int e = is_ex[j];
+        const bool has_cont = j < ex_back, j_valid = j < kend;
+        const double dj = disc[j];
+        if (e) {
+            for (int i = tid; i < n; i += BR_SMALL_NT) {
+                const double d = dj * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
+                double cont = 0.0;
+                if (has_cont) {
+                    double sum = 0.0;
+                    const uint64_t gid = path_offset + (uint64_t)i;
+                    const int32_t* row = inj ? inj + ((int64_t)(e - 1) * n + i) * n_br : nullptr;
+                    for (int b0 = 0; b0 < n_br; b0 += 4) {
+                        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                        if (!inj) u = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)j, 0x10000u + (uint32_t)(b0 >> 2), keys);
+                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (b0 + q < n_br) sum += F[inj ? (int)row[b0 + q] : (int)(((uint64_t)uu[q] * (uint64_t)n) >> 32)];
+                    }
+                    cont = sum / (double)n_br;
+                }
+                const double better = d < cont ? cont : d;
+                if (better > best[i]) best[i] = better;
+            }
+            __syncthreads();  // every gather of date j is done before F takes index j in
+        }
+        if (j_valid)
+            for (int i = tid; i < n; i += BR_SMALL_NT) {
+                const double d = dj * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
+                if (d > F[i]) F[i] = d;
+            }
+        __syncthreads();
+    }
+    double upper = 0.0;
+    for (int i = tid; i < n; i += BR_SMALL_NT) upper += best[i];
+    const double a0 = warp_sum(lower), a1 = warp_sum(upper);
+    if ((tid & 31) == 0) { red[tid >> 5][0] = a0; red[tid >> 5][1] = a1; }
+    __syncthreads();
+    if (tid < 2) {
+        double s = 0.0;
+        for (int w = 0; w < BR_SMALL_NT / 32; ++w) s += red[w][tid];
+        out[tid] = s;
+    }
+}
+
 __global__ void __launch_bounds__(PR_NT) sum_vector_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ partial) {
     double acc[1] = {0.0};
     for (int64_t i = (int64_t)blockIdx.x * PR_NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * PR_NT) acc[0] += v[i];
@@ -333,15 +409,17 @@ extern "C" int mcp_asymptotic_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     unsigned char* sb = (unsigned char*)ctx->scratch;
     double *d_tab = (double*)(sb + o_tab), *d_part = (double*)(sb + o_part), *d_out = (double*)(sb + o_out);
     cudaStream_t st = ctx->stream;
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), 2 * (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d_tab, tab.data(), 2 * (size_t)M * 8));
     MCP_TRY(fold_sum(ctx, d_part, grid, 2, d_out, [&] {
         if (ps->dtype == MCP_F32) asym_kernel<float><<<grid, PR_NT, 0, st>>>((const float*)ps->data, ps->ld, N, jend, d_tab, d_tab + M, strike, is_call, d_part);
         else asym_kernel<double><<<grid, PR_NT, 0, st>>>((const double*)ps->data, ps->ld, N, jend, d_tab, d_tab + M, strike, is_call, d_part);
     }));
     MCP_TRY(mcp_allreduce_f64(ctx, d_out, 2));
     double h[2] = {0, 0};
-    MCP_CUDA(ctx, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, st));
+    double* hp = (double*)mcp_stage_alloc(ctx, 16);
+    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_out, 16, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hp) memcpy(h, hp, 16);
     *price = h[1] > 0.0 ? h[0] / h[1] : 0.0;  // :108
     return MCP_OK;
 }
@@ -386,10 +464,10 @@ extern "C" int mcp_martingale_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     cudaStream_t st = ctx->stream;
     const bool f32 = ps->dtype == MCP_F32;
     const double nloc = (double)N;
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_df, DF.data(), (size_t)M * 8, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d_df, DF.data(), (size_t)M * 8));
     MCP_CUDA(ctx, cudaMemsetAsync(d_fin, 0, 8 * 8, st));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_fin + 1, &nloc, 8, cudaMemcpyHostToDevice, st));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_fin + 3, &nloc, 8, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d_fin + 1, &nloc, 8));
+    MCP_TRY(mcp_h2d(ctx, d_fin + 3, &nloc, 8));
 
     // pass 1: primal + regression samples
     MCP_TRY(fold_sum(ctx, d_part, grid, 1, d_fin, [&] {
@@ -431,8 +509,10 @@ extern "C" int mcp_martingale_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
         MCP_TRY(mcp_allreduce_f64(ctx, d_fin + 4, 1));
     }
     double h[8];
-    MCP_CUDA(ctx, cudaMemcpyAsync(h, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
+    double* hp = (double*)mcp_stage_alloc(ctx, 64);
+    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hp) memcpy(h, hp, 64);
     const double primal = h[0] / h[1];
     const double dual = max_iterations >= 2 ? h[4] / h[1] : primal;  // round 1 uses M = 0, offset = 0: dual == primal
     if (primal_out) *primal_out = primal;
@@ -474,12 +554,14 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_disc = take((size_t)M * 8), o_ex = take((size_t)(n_ex > 0 ? n_ex : 1) * 4), o_part = take((size_t)grid * PR_LD * 8), o_fin = take(4 * 8);
-    const size_t o_inj = take(injected_rp ? (size_t)N * num_branches * 4 : 0);
+    const size_t o_isex = take((size_t)M * 4);
+    const size_t o_inj = take(injected_rp ? (size_t)N * num_branches * 4 * (size_t)(N <= BR_SMALL_MAX && n_ex > 0 ? n_ex : 1) : 0);
     MCP_TRY(mcp_scratch_reserve(ctx, off));
     MCP_TRY(mcp_carry_reserve(ctx, (size_t)3 * ps->ld * 8));
     unsigned char* sb = (unsigned char*)ctx->scratch;
     double *d_disc = (double*)(sb + o_disc), *d_part = (double*)(sb + o_part), *d_fin = (double*)(sb + o_fin);
     int* d_ex = (int*)(sb + o_ex);
+    int* d_isex = (int*)(sb + o_isex);
     int32_t* d_inj = injected_rp ? (int32_t*)(sb + o_inj) : nullptr;
     double* F0 = (double*)ctx->carry;
     double* F1 = F0 + ps->ld;
@@ -487,19 +569,37 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
     cudaStream_t st = ctx->stream;
     const bool f32 = ps->dtype == MCP_F32;
     const double nloc = (double)N;
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_disc, disc.data(), (size_t)M * 8, cudaMemcpyHostToDevice, st));
-    if (n_ex > 0) MCP_CUDA(ctx, cudaMemcpyAsync(d_ex, exercise_times, (size_t)n_ex * 4, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d_disc, disc.data(), (size_t)M * 8));
+    if (n_ex > 0) MCP_TRY(mcp_h2d(ctx, d_ex, exercise_times, (size_t)n_ex * 4));
     MCP_CUDA(ctx, cudaMemsetAsync(d_fin, 0, 4 * 8, st));
-    MCP_CUDA(ctx, cudaMemcpyAsync(d_fin + 2, &nloc, 8, cudaMemcpyHostToDevice, st));
+    MCP_TRY(mcp_h2d(ctx, d_fin + 2, &nloc, 8));
     MCP_CUDA(ctx, cudaMemsetAsync(F0, 0, (size_t)3 * ps->ld * 8, st));
 
+    const PhiloxKeys keys = philox_make_keys(seed);
+    const bool small = N <= BR_SMALL_MAX && !(ctx->nranks > 1 && ctx->comm) && !getenv("MCP_BRANCH_PER_DATE") && n_ex > 0;
+    if (small) {
+        // one launch: both bounds
+        MCP_TRY(mcp_h2d(ctx, d_isex, is_ex.data(), (size_t)M * 4));
+        if (d_inj) MCP_CUDA(ctx, cudaMemcpyAsync(d_inj, injected_rp, (size_t)n_ex * N * num_branches * 4, cudaMemcpyHostToDevice, st));
+        const int j_hi = kend - 1 > exercise_times[n_ex - 1] ? kend - 1 : exercise_times[n_ex - 1];
+        const size_t smem = (size_t)2 * N * sizeof(double);
+        if (f32) {
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)branch_small_kernel<float>, BR_SMALL_NT, (size_t)2 * BR_SMALL_MAX * sizeof(double), nullptr));
+            branch_small_kernel<float><<<1, BR_SMALL_NT, smem, st>>>((const float*)ps->data, ps->ld, (int)N, j_hi, exercise_times[0], kend, ex_back, d_isex, d_ex, n_ex,
+                                                                   d_disc, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
+        } else {
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)branch_small_kernel<double>, BR_SMALL_NT, (size_t)2 * BR_SMALL_MAX * sizeof(double), nullptr));
+            branch_small_kernel<double><<<1, BR_SMALL_NT, smem, st>>>((const double*)ps->data, ps->ld, (int)N, j_hi, exercise_times[0], kend, ex_back, d_isex, d_ex, n_ex,
+                                                                    d_disc, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
+        }
+        MCP_LAUNCH_CHECK(ctx);
+    } else {
     // lower bound
     MCP_TRY(fold_sum(ctx, d_part, grid, 1, d_fin, [&] {
         if (f32) branch_lower_kernel<float><<<grid, PR_NT, 0, st>>>((const float*)ps->data, ps->ld, N, d_ex, n_ex, d_disc, strike, is_call, d_part);
         else branch_lower_kernel<double><<<grid, PR_NT, 0, st>>>((const double*)ps->data, ps->ld, N, d_ex, n_ex, d_disc, strike, is_call, d_part);
     }));
     // upper bound: descending sweep from the last index any loop can touch down to the first exercise date
-    const PhiloxKeys keys = philox_make_keys(seed);
     if (n_ex > 0) {
         const int j_hi = kend - 1 > exercise_times[n_ex - 1] ? kend - 1 : exercise_times[n_ex - 1];
         double *Fo = F0, *Fn = F1;
@@ -522,10 +622,13 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
         }
     }
     MCP_TRY(fold_sum(ctx, d_part, grid, 1, d_fin + 1, [&] { sum_vector_kernel<<<grid, PR_NT, 0, st>>>(d_best, N, d_part); }));
+    }
     MCP_TRY(mcp_allreduce_f64(ctx, d_fin, 3));
     double h[3];
-    MCP_CUDA(ctx, cudaMemcpyAsync(h, d_fin, 24, cudaMemcpyDeviceToHost, st));
+    double* hp = (double*)mcp_stage_alloc(ctx, 24);
+    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_fin, 24, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hp) memcpy(h, hp, 24);
     const double lower = h[0] / h[2], upper = h[1] / h[2];
     if (lower_out) *lower_out = lower;
     if (upper_out) *upper_out = upper;

@@ -163,3 +163,21 @@ def test_prediction_gen_row_through_the_python_plugins(engine, port):
     assert lsm == pytest.approx(port.lsm(paths, r, K, T, dt, False, 2)["price"], rel=1e-9)
     assert mo == pytest.approx(port.martingale(paths, r, K, T, dt, False, 2, 5)["price"], rel=1e-8)
     assert 0.0 < bp < 3 * max(aa, lsm)
+
+
+def test_branching_single_launch_equals_per_date_kernels(engine, gold, monkeypatch):
+    """<= 4096 paths: both bounds in one single-CTA launch; same resampling stream, same values as the per-date path."""
+    _, P = gold
+    ex = np.arange(0, 50)
+    for n_paths, dtype in ((250, m.MCP_F64), (3000, m.MCP_F32)):
+        ps = engine.upload_paths(P[:n_paths], dtype=dtype)
+        l0 = engine.launch_count
+        one = engine.branching_price(ps, 0.05, 100.0, 0.9, 0.02, False, 10, ex, seed=4, want_bounds=True)
+        assert engine.launch_count - l0 <= 2
+        monkeypatch.setenv("MCP_BRANCH_PER_DATE", "1")
+        l0 = engine.launch_count
+        many = engine.branching_price(ps, 0.05, 100.0, 0.9, 0.02, False, 10, ex, seed=4, want_bounds=True)
+        assert engine.launch_count - l0 > 40
+        monkeypatch.delenv("MCP_BRANCH_PER_DATE")
+        ps.close()
+        assert one[1] == pytest.approx(many[1], rel=1e-14) and one[2] == pytest.approx(many[2], rel=1e-13)
