@@ -18,6 +18,7 @@
  *   mcp_estimate_rbergomi_params  RoughVolatility::estimateXi/H/Eta/Rho     src/models/RoughVolatility.cpp:72-169, :324-331
  *   mcp_generate_stock_price_paths  GenerateStockPricePaths, exact call shape  src/core/PredictionGen.cpp:736-737
  *   mcp_price_surface_rbergomi_lsm  [new] the row loop of src/core/PredictionGen.cpp:542-866 for a strike x maturity grid
+ *   mcp_price_rows              the whole per-row block of src/core/PredictionGen.cpp:700-791, batched over rows
  *   mcp_asymptotic_price        AsymptoticAnalysis::PredictOptionPrice      include/models/AsymptoticAnalysisPricer.h:8-15
  *   mcp_martingale_price        MartingaleOptimization::PredictOptionPrice  include/models/MartingaleOptimizationPricer.h:10-18
  *   mcp_branching_price         BranchingProcesses::PredictOptionPrice      include/models/BranchingProcessPricer.h:8-16
@@ -172,6 +173,26 @@ int mcp_price_surface_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *mode
                                    int steps_per_year, int64_t n_paths, uint64_t seed, uint64_t path_offset,
                                    int mat_first, int mat_stride, double *prices, double *std_errors /*nullable*/,
                                    float *gen_ms_total /*nullable*/, float *lsm_ms_total /*nullable*/);
+
+/* ------------------------------------------------------------------------ batched row driver
+ * The reference's row loop (src/core/PredictionGen.cpp:542-866) as one call: for every row, n_paths (<= 4096; the
+ * reference uses 250, :719) rough-vol paths of row.n_steps steps (<= 512) are generated and priced by all four
+ * pricers with the reference's per-row settings (exercise dates 0 .. n_steps-1, :780-783).  Three kernel launches per
+ * batch instead of several per row and pricer.  Paths of row k are keyed by (seed, path_offset + k * n_paths + i), i.e.
+ * the paths mcp_gen_rbergomi(.., seed, path_offset + k * n_paths) generates. */
+typedef struct mcp_row {
+    mcp_rbergomi_params model; /* from mcp_estimate_rbergomi_params(history) or explicit */
+    int n_steps;               /* floor(maturity * 252) in the reference (:718); rows with n_steps < 1 yield zeros (:720-733) */
+    int is_call;
+    double r, strike, maturity, dt, sigma, dividend;
+} mcp_row;
+typedef struct mcp_row_result {
+    double asymptotic, branching, lsm, martingale; /* the four columns PredictionGen appends (:809-815) */
+    double lsm_std_error;
+} mcp_row_result;
+int mcp_price_rows(mcp_ctx *ctx, const mcp_row *rows, int n_rows, int n_paths, int poly_order, int num_branches,
+                   int max_iterations, uint64_t seed, uint64_t path_offset, mcp_row_result *out,
+                   float *gen_ms /*nullable*/, float *price_ms /*nullable*/);
 
 /* ------------------------------------------------------------- exact-signature generator
  * Host estimators of the reference (pure host arithmetic, no device needed): xi = var(logret)/dt, H = DFA slope

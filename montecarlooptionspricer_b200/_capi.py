@@ -33,6 +33,16 @@ class LsmResult(C.Structure):
                 ("n_paths_global", C.c_int64), ("elapsed_ms", C.c_float), ("n_kernel_launches", C.c_int)]
 
 
+class Row(C.Structure):
+    _fields_ = [("model", RbergomiParams), ("n_steps", C.c_int), ("is_call", C.c_int), ("r", C.c_double), ("strike", C.c_double),
+                ("maturity", C.c_double), ("dt", C.c_double), ("sigma", C.c_double), ("dividend", C.c_double)]
+
+
+class RowResult(C.Structure):
+    _fields_ = [("asymptotic", C.c_double), ("branching", C.c_double), ("lsm", C.c_double), ("martingale", C.c_double),
+                ("lsm_std_error", C.c_double)]
+
+
 class Profile(C.Structure):
     _fields_ = [("gen_kernel_ms", C.c_float), ("sweep_kernels_ms", C.c_float), ("n_sweep_launches", C.c_int),
                 ("lsm_total_ms", C.c_float)]
@@ -80,6 +90,8 @@ SIGNATURES = {
                                          C.c_uint64, C.c_uint64, C.POINTER(LsmResult), _fp]),
     "mcp_price_surface_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), _dp, C.c_int, _dp, C.c_int,
                                                  C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp, _dp, _fp, _fp]),
+    "mcp_price_rows": (C.c_int, [_vp, C.POINTER(Row), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                 C.POINTER(RowResult), _fp, _fp]),
     "mcp_estimate_rbergomi_params": (C.c_int, [_dp, C.c_int64, C.POINTER(RbergomiParams)]),
     "mcp_generate_stock_price_paths": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                                  C.POINTER(_dp)]),

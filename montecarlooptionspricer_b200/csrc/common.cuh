@@ -120,3 +120,7 @@ cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i);
     } while (0)
 
 static inline int64_t mcp_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// batched row generation (gen_rbergomi.cu), used by rows.cu
+int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t model_stride_bytes, const int* n_steps, int n_rows, int n_paths,
+                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld);

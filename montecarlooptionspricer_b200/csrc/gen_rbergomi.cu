@@ -197,10 +197,10 @@ __device__ __forceinline__ void native_normals(uint32_t c0, uint32_t c1, int k, 
 // Dynamic shared memory carve-up (per CTA):
 //   float2 A[Mp][TP] | float W[Mp][TP] | float tot[G][TP] | float2 phis[Mp] | float2 tw[Mp] | float comp2[Mp] | int rev[Mp]
 template <int TP, bool INJECT, bool DUMP>
-__global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
-                                                              const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
-                                                              const int* __restrict__ g_rev, const float* __restrict__ draws_in,
-                                                              float* __restrict__ draws_out, float* __restrict__ out) {
+__device__ __forceinline__ void rbergomi_tiles(const RbParams& P, const PhiloxKeys& K, const float2* __restrict__ g_phis,
+                                               const float2* __restrict__ g_tw, const float* __restrict__ g_comp2, const int* __restrict__ g_rev,
+                                               const float* __restrict__ draws_in, float* __restrict__ draws_out, float* __restrict__ out,
+                                               int64_t tile0, int64_t tile_stride) {
     constexpr int G = NT / TP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Mp = P.Mp, n = P.n;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
     const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
     __syncthreads();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
         const int64_t path = tile * TP + p;  // local path index in this slab
         const bool live = path < P.n_paths;
         const uint64_t gid = P.path_offset + (uint64_t)path;
@@ -365,6 +365,34 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, Philo
         }
         __syncthreads();  // A / W / tot are rewritten by the next tile
     }
+}
+
+template <int TP, bool INJECT, bool DUMP>
+__global__ void __launch_bounds__(NT, 2) rbergomi_paths_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
+                                                              const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
+                                                              const int* __restrict__ g_rev, const float* __restrict__ draws_in,
+                                                              float* __restrict__ draws_out, float* __restrict__ out) {
+    rbergomi_tiles<TP, INJECT, DUMP>(P, K, g_phis, g_tw, g_comp2, g_rev, draws_in, draws_out, out, blockIdx.x, gridDim.x);
+}
+
+// Batched rows (rows.cu): blockIdx.y = row, every row with its own parameters, tables (phis | tw | comp2 | rev, packed
+// like the single-row scratch) and slab; blockIdx.x strides over the row's 32-path tiles.
+struct RbRow {
+    RbParams P;
+    int64_t table_off;  // bytes into `tables`
+    int64_t slab_off;   // floats into `slabs`
+};
+
+__global__ void __launch_bounds__(NT, 2) rbergomi_rows_kernel(const RbRow* __restrict__ rows, PhiloxKeys K, const unsigned char* __restrict__ tables,
+                                                             float* __restrict__ slabs) {
+    const RbRow& R = rows[blockIdx.y];
+    const int Mp = R.P.Mp;
+    const unsigned char* t = tables + R.table_off;
+    const float2* phis = reinterpret_cast<const float2*>(t);
+    const float2* tw = phis + Mp;
+    const float* comp2 = reinterpret_cast<const float*>(tw + Mp);
+    const int* rev = reinterpret_cast<const int*>(comp2 + Mp);
+    rbergomi_tiles<32, false, false>(R.P, K, phis, tw, comp2, rev, nullptr, nullptr, slabs + R.slab_off, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -743,5 +771,67 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         }
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return MCP_OK;
+}
+
+// Batched generation for the row driver (rows.cu): row r = its own model, step count and slab; normals of path i of
+// row r are keyed by (seed, path_offset + r * n_paths + i) -- exactly what mcp_gen_rbergomi produces for that row
+// when called with path_offset + r * n_paths.  One launch for all rows.
+int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t model_stride_bytes, const int* n_steps, int n_rows, int n_paths,
+                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld) {
+    std::vector<RbRow> rows((size_t)n_rows);
+    std::vector<unsigned char> tables;
+    int max_Mp = 1, live_rows = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const mcp_rbergomi_params* prm = (const mcp_rbergomi_params*)((const unsigned char*)models + (size_t)r * model_stride_bytes);
+        RbRow& R = rows[(size_t)r];
+        memset(&R, 0, sizeof(R));
+        const int n = n_steps[r];
+        if (n < 1) { R.P.n_paths = 0; R.P.Mp = 1; continue; }  // no tiles: the kernel's tile loop is empty
+        if (n > 512) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: n_steps %d > 512", n);
+        if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0))
+            return mcp_fail(ctx, MCP_ERR_DOMAIN, "rows: row %d needs dt > 0, H >= 0, |rho| <= 1, xi >= 0", r);
+        std::vector<float> phis, tw, comp2;
+        std::vector<int> pos;
+        mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &R.P.Mp, &R.P.lgMp, &R.P.lg_radix, &R.P.n_stage);
+        const int Mp = R.P.Mp;
+        const double log2e = 1.4426950408889634074;
+        R.P.S0 = (float)prm->S0;
+        R.P.rd2 = (float)(prm->r * prm->dt * log2e);
+        R.P.nkq = (float)(-0.5 / log2e);
+        R.P.lsq = (float)log2(sqrt(prm->dt) * log2e);
+        R.P.rho = (float)prm->rho;
+        R.P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);
+        R.P.n = n;
+        R.P.n_paths = n_paths;
+        R.P.ld = ld;
+        R.P.path_offset = path_offset + (uint64_t)r * (uint64_t)n_paths;
+        R.P.ld_draws = 0;
+        R.table_off = (int64_t)tables.size();
+        R.slab_off = (int64_t)r * slab_stride;
+        const size_t o = tables.size();
+        tables.resize(o + (size_t)Mp * 24);
+        memcpy(tables.data() + o, phis.data(), (size_t)Mp * 8);
+        memcpy(tables.data() + o + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
+        memcpy(tables.data() + o + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
+        memcpy(tables.data() + o + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
+        if (Mp > max_Mp) max_Mp = Mp;
+        ++live_rows;
+    }
+    if (live_rows == 0) return MCP_OK;
+    const size_t rows_bytes = (size_t)n_rows * sizeof(RbRow);
+    const size_t need = mcp_round_up((int64_t)rows_bytes, 256) + tables.size();
+    MCP_TRY(mcp_scratch_reserve(ctx, need));
+    unsigned char* base = (unsigned char*)ctx->scratch;
+    MCP_CUDA(ctx, cudaMemcpyAsync(base, rows.data(), rows_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaMemcpyAsync(base + mcp_round_up((int64_t)rows_bytes, 256), tables.data(), tables.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    const size_t smem = smem_bytes(max_Mp, 32);
+    if (smem > 227 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: transform of %d points does not fit", max_Mp);
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)rbergomi_rows_kernel, NT, smem, nullptr));
+    const PhiloxKeys K = philox_make_keys(seed);
+    const dim3 grid((unsigned)((n_paths + 31) / 32), (unsigned)n_rows);
+    rbergomi_rows_kernel<<<grid, NT, smem, ctx->stream>>>((const RbRow*)base, K, base + mcp_round_up((int64_t)rows_bytes, 256), slabs);
+    MCP_LAUNCH_CHECK(ctx);
     return MCP_OK;
 }

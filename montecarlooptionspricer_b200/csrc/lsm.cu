@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "lsm_solve.cuh"
+#include "small_bodies.cuh"
 
 namespace {
 
@@ -877,104 +878,17 @@ __global__ void lsm_fill_tau_kernel(int32_t* __restrict__ tau, int64_t n, int32_
 // step matters twice for the row loop of the reference: per-row latency, and the launch stream of 16 host threads no
 // longer serialises on the driver.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SMALL_NT = 512;
-constexpr int SMALL_MAX_PATHS = 4096;
-
-template <int NV>
-__device__ __forceinline__ void small_block_sum(double (&acc)[NV], double* __restrict__ out /* shared [NV] */) {
-    __shared__ double red[SMALL_NT / 32][NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const double s = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < SMALL_NT / 32; ++w) s += red[w][threadIdx.x];
-        out[threadIdx.x] = s;
-    }
-    __syncthreads();
-}
+constexpr int SMALL_NT = SB_NT;
+constexpr int SMALL_MAX_PATHS = SB_MAX_PATHS;
 
 template <typename ST, int P>
-__global__ void __launch_bounds__(SMALL_NT, 1) lsm_small_kernel(SweepArgs a, int M) {
-    constexpr int NM = 3 * P + 2;
-    constexpr int NV = NM > 2 ? NM : 2;
+__global__ void __launch_bounds__(SB_NT, 1) lsm_small_kernel(SweepArgs a, int M, double dt, double maturity) {
     extern __shared__ double sV[];  // carry [n]
-    __shared__ double mom[NV], cf[COEF_LD], fin_s[2];
-    const ST* __restrict__ S = reinterpret_cast<const ST*>(a.S);
-    const int n = (int)a.n, tid = threadIdx.x;
-    auto ldS = [&](int j, int i) -> double { return (double)S[(int64_t)j * a.ld + i]; };
-
-    for (int i = tid; i < n; i += SMALL_NT) sV[i] = payoff_fn(a.is_call, ldS(M - 1, i), a.K);  // LSMPricer.cpp:37-40
-    __syncthreads();
-    for (int j = M - 2; j >= 0; --j) {                                                          // :42
-        if (a.d.kind[j] == STEP_DISCOUNT) {                                                     // :43-49
-            for (int i = tid; i < n; i += SMALL_NT) sV[i] *= a.disc;
-            __syncthreads();
-            continue;
-        }
-        const double mu = a.d.mu[j], inv_s = a.d.inv_s[j];
-        double acc[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        for (int i = tid; i < n; i += SMALL_NT) {
-            const double s = ldS(j, i);
-            if (payoff_fn(a.is_call, s, a.K) > 1e-14) {                                         // :51-58
-                const double x = (s - mu) * inv_s, y = sV[i] * a.disc;                          // :69
-                double xp = x;
-                acc[0] += 1.0;
-                acc[2 * P + 1] += y;
-#pragma unroll
-                for (int k = 1; k <= 2 * P; ++k) {
-                    acc[k] += xp;
-                    if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
-                    if (k < 2 * P) xp *= x;
-                }
-            }
-        }
-        small_block_sum<NV>(acc, mom);
-        if (tid == 0) {
-            solve_normal_equations<P>(mom, a.d.coef + (int64_t)j * COEF_LD);                    // :76
-            for (int k = 0; k < COEF_LD; ++k) cf[k] = a.d.coef[(int64_t)j * COEF_LD + k];
-        }
-        __syncthreads();
-        double c[P + 1];
-#pragma unroll
-        for (int k = 0; k <= P; ++k) c[k] = cf[k];
-        for (int i = tid; i < n; i += SMALL_NT) {
-            const double s = ldS(j, i), pay = payoff_fn(a.is_call, s, a.K);
-            const double x = (s - mu) * inv_s;
-            double cont = c[P];
-#pragma unroll
-            for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
-            const bool itm = pay > 1e-14, ex = !(pay < cont);                                   // :55, :85
-            const double carried = pay < 1e-14 ? sV[i] * a.disc : 0.0;                          // :89-94; == 1e-14 keeps the initial 0 (:35)
-            sV[i] = itm ? (ex ? pay : cont) : carried;
-            if (a.tau && itm && ex) a.tau[i] = j;
-        }
-        __syncthreads();
-    }
-    // payoff averaging (:97-101) + two-pass standard error
-    double t[2] = {0.0, 0.0};
-    for (int i = tid; i < n; i += SMALL_NT) t[0] += sV[i];
-    small_block_sum<2>(t, fin_s);
-    const double mean = fin_s[0] / (double)n;
-    double q[2] = {0.0, 0.0};
-    for (int i = tid; i < n; i += SMALL_NT) {
-        const double dlt = sV[i] - mean;
-        q[0] = fma(dlt, dlt, q[0]);
-        reinterpret_cast<double*>(a.V)[i] = sV[i];
-    }
-    __shared__ double fin_q[2];
-    small_block_sum<2>(q, fin_q);
-    if (tid == 0) { a.d.fin[0] = fin_s[0]; a.d.fin[1] = fin_q[0]; a.d.fin[2] = (double)n; }
+    sb_lsm<ST, P>(reinterpret_cast<const ST*>(a.S), a.ld, (int)a.n, M, a.K, a.is_call, a.disc, dt, maturity, sV, a.tau, a.d.coef, a.d.mu, a.d.inv_s,
+                  reinterpret_cast<double*>(a.V), a.d.fin);
 }
 
-typedef void (*SmallFn)(SweepArgs, int);
+typedef void (*SmallFn)(SweepArgs, int, double, double);
 template <typename ST>
 SmallFn pick_small(int p) {
     switch (p) {
@@ -1167,13 +1081,16 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     MCP_CUDA(ctx, cudaMemsetAsync(d.counter, 0, 4, st));
 
     // ---- standardisation tables from a fixed leading sample of this rank's paths (summed over ranks) ----
-    const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
-    if (ps->dtype == MCP_F32) lsm_scale_sums_kernel<float><<<M, 256, 0, st>>>((const float*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
-    else lsm_scale_sums_kernel<double><<<M, 256, 0, st>>>((const double*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
-    MCP_LAUNCH_CHECK(ctx);
-    MCP_TRY(mcp_allreduce_f64(ctx, d.ssum, M * 4));
-    lsm_scale_finalize_kernel<<<(M + 127) / 128, 128, 0, st>>>(d.ssum, M, prm->strike, d.mu, d.inv_s);
-    MCP_LAUNCH_CHECK(ctx);
+    // (the single-launch kernel standardises each step itself, from all of its in-the-money prices)
+    if (!small) {
+        const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
+        if (ps->dtype == MCP_F32) lsm_scale_sums_kernel<float><<<M, 256, 0, st>>>((const float*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
+        else lsm_scale_sums_kernel<double><<<M, 256, 0, st>>>((const double*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
+        MCP_LAUNCH_CHECK(ctx);
+        MCP_TRY(mcp_allreduce_f64(ctx, d.ssum, M * 4));
+        lsm_scale_finalize_kernel<<<(M + 127) / 128, 128, 0, st>>>(d.ssum, M, prm->strike, d.mu, d.inv_s);
+        MCP_LAUNCH_CHECK(ctx);
+    }
     if (dTau) {
         lsm_fill_tau_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dTau, N, (int32_t)(M - 1));
         MCP_LAUNCH_CHECK(ctx);
@@ -1220,7 +1137,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         const size_t smem = (size_t)N * sizeof(double);
         MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, SMALL_NT, (size_t)SMALL_MAX_PATHS * sizeof(double), nullptr));
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 0), st);
-        fn<<<1, SMALL_NT, smem, st>>>(a, M);
+        fn<<<1, SMALL_NT, smem, st>>>(a, M, prm->dt, prm->maturity);
         MCP_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 1), st);
     }

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "lsm_solve.cuh"
 #include "philox.cuh"
+#include "small_bodies.cuh"
 
 namespace {
 
@@ -271,79 +272,51 @@ __global__ void __launch_bounds__(PR_NT) branch_upper_kernel(const ST* __restric
     }
 }
 
-// Both bounds in ONE launch for small path sets (<= 4096 paths: the reference's rows are 250): a single CTA keeps the
-// suffix maxima F and the running best in shared memory and walks the time indices downwards with block barriers
-// (gather from F, barrier, update F).  Same resampling stream and arithmetic as the per-date kernels above.
-constexpr int BR_SMALL_NT = 512;
-constexpr int BR_SMALL_MAX = 4096;
+// Single-launch forms for small path sets (<= 4096 paths: the reference's rows are 250): one CTA runs the whole
+// pricer out of shared memory (small_bodies.cuh).  Same arithmetic and, for Branching, the same resampling stream as
+// the streaming kernels above.
+constexpr int BR_SMALL_NT = SB_NT;
+constexpr int BR_SMALL_MAX = SB_MAX_PATHS;
 
 template <typename ST>
-__global__ void __launch_bounds__(BR_SMALL_NT, 1) branch_small_kernel(const ST* __restrict__ S, int64_t ld, int n, int j_hi, int j_lo, int kend, int ex_back,
-                                                                     const int* __restrict__ is_ex, const int* __restrict__ ex, int n_ex,
-                                                                     const double* __restrict__ disc, double K, int is_call, int n_br, PhiloxKeys keys,
-                                                                     uint64_t path_offset, const int32_t* __restrict__ inj, double* __restrict__ out) {
+__global__ void __launch_bounds__(SB_NT, 1) branch_small_kernel(const ST* __restrict__ S, int64_t ld, int n, int j_hi, int j_lo, int kend, int ex_back,
+                                                               const int* __restrict__ is_ex, const int* __restrict__ ex, int n_ex, double r, double dt,
+                                                               double K, int is_call, int n_br, PhiloxKeys keys, uint64_t path_offset,
+                                                               const int32_t* __restrict__ inj, double* __restrict__ out) {
     extern __shared__ double sm[];  // F[n] | best[n]
-    double* F = sm;
-    double* best = sm + n;
-    __shared__ double red[BR_SMALL_NT / 32][2];
-    const int tid = threadIdx.x;
-    double lower = 0.0;
-    for (int i = tid; i < n; i += BR_SMALL_NT) {
-        F[i] = 0.0;
-        best[i] = 0.0;
-        double b = 0.0;  // lower bound: first listed date with a positive discounted payoff (:55-70)
-        for (int e = 0; e < n_ex; ++e) {
-            const int j = ex[e];
-            const double d = disc[j] * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
-            if (d > b) { b = d; break; }
-        }
-        lower += b;
+    sb_branching<ST>(S, ld, n, j_hi, j_lo, kend, ex_back, is_ex, ex, n_ex, r, dt, K, is_call, n_br, keys, path_offset, inj, sm, sm + n, out);
+}
+
+template <typename ST>
+__global__ void __launch_bounds__(SB_NT, 1) asym_small_kernel(const ST* __restrict__ S, int64_t ld, int n, int M, double K, int is_call, double r, double dt,
+                                                             double maturity, double sigma, double dividend, double* __restrict__ out) {
+    extern __shared__ double sm[];  // boundary[M] | discount[M]
+    sb_asymptotic<ST>(S, ld, n, M, K, is_call, r, dt, maturity, sigma, dividend, sm, out);
+}
+
+template <typename ST, int P>
+__global__ void __launch_bounds__(SB_NT, 1) mart_small_kernel(const ST* __restrict__ S, int64_t ld, int n, int M, double K, int is_call, double r, double dt,
+                                                             double maturity, int max_iterations, double* __restrict__ out) {
+    extern __shared__ double sm[];  // samples[4 n] | DF[M]
+    sb_martingale<ST, P>(S, ld, n, M, K, is_call, r, dt, maturity, max_iterations, sm, sm + 4 * (size_t)n, out);
+}
+
+typedef void (*MartSmallFn)(const void*, int64_t, int, int, double, int, double, double, double, int, double*);
+template <typename ST>
+MartSmallFn pick_mart_small(int p) {
+    switch (p) {
+        case 0: return (MartSmallFn)mart_small_kernel<ST, 0>;
+        case 1: return (MartSmallFn)mart_small_kernel<ST, 1>;
+        case 2: return (MartSmallFn)mart_small_kernel<ST, 2>;
+        case 3: return (MartSmallFn)mart_small_kernel<ST, 3>;
+        case 4: return (MartSmallFn)mart_small_kernel<ST, 4>;
+        case 5: return (MartSmallFn)mart_small_kernel<ST, 5>;
+        default: return (MartSmallFn)mart_small_kernel<ST, 6>;
     }
-    __syncthreads();
-    for (int j = j_hi; j >= j_lo; --j) {
-        const int e = is_ex[j];
-        const bool has_cont = j < ex_back, j_valid = j < kend;
-        const double dj = disc[j];
-        if (e) {
-            for (int i = tid; i < n; i += BR_SMALL_NT) {
-                const double d = dj * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
-                double cont = 0.0;
-                if (has_cont) {
-                    double sum = 0.0;
-                    const uint64_t gid = path_offset + (uint64_t)i;
-                    const int32_t* row = inj ? inj + ((int64_t)(e - 1) * n + i) * n_br : nullptr;
-                    for (int b0 = 0; b0 < n_br; b0 += 4) {
-                        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-                        if (!inj) u = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)j, 0x10000u + (uint32_t)(b0 >> 2), keys);
-                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (b0 + q < n_br) sum += F[inj ? (int)row[b0 + q] : (int)(((uint64_t)uu[q] * (uint64_t)n) >> 32)];
-                    }
-                    cont = sum / (double)n_br;
-                }
-                const double better = d < cont ? cont : d;
-                if (better > best[i]) best[i] = better;
-            }
-            __syncthreads();  // every gather of date j is done before F takes index j in
-        }
-        if (j_valid)
-            for (int i = tid; i < n; i += BR_SMALL_NT) {
-                const double d = dj * payoff_fn(is_call, ldS<ST>(S + (int64_t)j * ld + i), K);
-                if (d > F[i]) F[i] = d;
-            }
-        __syncthreads();
-    }
-    double upper = 0.0;
-    for (int i = tid; i < n; i += BR_SMALL_NT) upper += best[i];
-    const double a0 = warp_sum(lower), a1 = warp_sum(upper);
-    if ((tid & 31) == 0) { red[tid >> 5][0] = a0; red[tid >> 5][1] = a1; }
-    __syncthreads();
-    if (tid < 2) {
-        double s = 0.0;
-        for (int w = 0; w < BR_SMALL_NT / 32; ++w) s += red[w][tid];
-        out[tid] = s;
-    }
+}
+
+bool use_small(const mcp_ctx* ctx, int64_t N, int M) {
+    return N <= SB_MAX_PATHS && M <= 4096 && !(ctx->nranks > 1 && ctx->comm) && !getenv("MCP_PRICERS_STREAMING");
 }
 
 __global__ void __launch_bounds__(PR_NT) sum_vector_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ partial) {
@@ -409,11 +382,23 @@ extern "C" int mcp_asymptotic_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     unsigned char* sb = (unsigned char*)ctx->scratch;
     double *d_tab = (double*)(sb + o_tab), *d_part = (double*)(sb + o_part), *d_out = (double*)(sb + o_out);
     cudaStream_t st = ctx->stream;
+    if (use_small(ctx, N, M)) {
+        const size_t smem = 2 * (size_t)M * sizeof(double);
+        if (ps->dtype == MCP_F32) {
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)asym_small_kernel<float>, SB_NT, 2 * 4096 * sizeof(double), nullptr));
+            asym_small_kernel<float><<<1, SB_NT, smem, st>>>((const float*)ps->data, ps->ld, (int)N, M, strike, is_call, r, dt, maturity, sigma, dividend, d_out);
+        } else {
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)asym_small_kernel<double>, SB_NT, 2 * 4096 * sizeof(double), nullptr));
+            asym_small_kernel<double><<<1, SB_NT, smem, st>>>((const double*)ps->data, ps->ld, (int)N, M, strike, is_call, r, dt, maturity, sigma, dividend, d_out);
+        }
+        MCP_LAUNCH_CHECK(ctx);
+    } else {
     MCP_TRY(mcp_h2d(ctx, d_tab, tab.data(), 2 * (size_t)M * 8));
     MCP_TRY(fold_sum(ctx, d_part, grid, 2, d_out, [&] {
         if (ps->dtype == MCP_F32) asym_kernel<float><<<grid, PR_NT, 0, st>>>((const float*)ps->data, ps->ld, N, jend, d_tab, d_tab + M, strike, is_call, d_part);
         else asym_kernel<double><<<grid, PR_NT, 0, st>>>((const double*)ps->data, ps->ld, N, jend, d_tab, d_tab + M, strike, is_call, d_part);
     }));
+    }
     MCP_TRY(mcp_allreduce_f64(ctx, d_out, 2));
     double h[2] = {0, 0};
     double* hp = (double*)mcp_stage_alloc(ctx, 16);
@@ -469,6 +454,24 @@ extern "C" int mcp_martingale_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     MCP_TRY(mcp_h2d(ctx, d_fin + 1, &nloc, 8));
     MCP_TRY(mcp_h2d(ctx, d_fin + 3, &nloc, 8));
 
+    if (use_small(ctx, N, M)) {
+        // one launch: d_fin[0] = primal sum, d_fin[4] = dual sum (laid out like the streaming path's results)
+        const size_t smem = (4 * (size_t)N + (size_t)M) * sizeof(double);
+        MartSmallFn fn = f32 ? pick_mart_small<float>(p) : pick_mart_small<double>(p);
+        MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, SB_NT, (4 * (size_t)SB_MAX_PATHS + 4096) * sizeof(double), nullptr));
+        fn<<<1, SB_NT, smem, st>>>(ps->data, ps->ld, (int)N, M, strike, is_call, r, dt, maturity, max_iterations, d_fin + 5);
+        MCP_LAUNCH_CHECK(ctx);
+        double h2[8];
+        double* hp2 = (double*)mcp_stage_alloc(ctx, 64);
+        MCP_CUDA(ctx, cudaMemcpyAsync(hp2 ? hp2 : h2, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, cudaStreamSynchronize(st));
+        if (hp2) memcpy(h2, hp2, 64);
+        const double primal = h2[5] / (double)N, dual = h2[6] / (double)N;
+        if (primal_out) *primal_out = primal;
+        if (dual_out) *dual_out = dual;
+        *price = 0.5 * (primal + dual);  // :63
+        return MCP_OK;
+    }
     // pass 1: primal + regression samples
     MCP_TRY(fold_sum(ctx, d_part, grid, 1, d_fin, [&] {
         if (f32) mart_primal_kernel<float><<<grid, PR_NT, 0, st>>>((const float*)ps->data, ps->ld, N, M, jend, d_df, strike, is_call, d_smp, d_part);
@@ -576,7 +579,7 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
     MCP_CUDA(ctx, cudaMemsetAsync(F0, 0, (size_t)3 * ps->ld * 8, st));
 
     const PhiloxKeys keys = philox_make_keys(seed);
-    const bool small = N <= BR_SMALL_MAX && !(ctx->nranks > 1 && ctx->comm) && !getenv("MCP_BRANCH_PER_DATE") && n_ex > 0;
+    const bool small = use_small(ctx, N, M) && !getenv("MCP_BRANCH_PER_DATE") && n_ex > 0;
     if (small) {
         // one launch: both bounds
         MCP_TRY(mcp_h2d(ctx, d_isex, is_ex.data(), (size_t)M * 4));
@@ -586,11 +589,11 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
         if (f32) {
             MCP_TRY(mcp_kernel_config(ctx, (const void*)branch_small_kernel<float>, BR_SMALL_NT, (size_t)2 * BR_SMALL_MAX * sizeof(double), nullptr));
             branch_small_kernel<float><<<1, BR_SMALL_NT, smem, st>>>((const float*)ps->data, ps->ld, (int)N, j_hi, exercise_times[0], kend, ex_back, d_isex, d_ex, n_ex,
-                                                                   d_disc, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
+                                                                   r, dt, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
         } else {
             MCP_TRY(mcp_kernel_config(ctx, (const void*)branch_small_kernel<double>, BR_SMALL_NT, (size_t)2 * BR_SMALL_MAX * sizeof(double), nullptr));
             branch_small_kernel<double><<<1, BR_SMALL_NT, smem, st>>>((const double*)ps->data, ps->ld, (int)N, j_hi, exercise_times[0], kend, ex_back, d_isex, d_ex, n_ex,
-                                                                    d_disc, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
+                                                                    r, dt, strike, is_call, num_branches, keys, path_offset, d_inj, d_fin);
         }
         MCP_LAUNCH_CHECK(ctx);
     } else {

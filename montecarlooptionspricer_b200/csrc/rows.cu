@@ -1,0 +1,169 @@
+// rows.cu -- the reference's row loop as ONE batch: src/core/PredictionGen.cpp:542-866 prices every CSV row with
+// 250 fresh paths (:719) through four pricers (:788-791), one row per OpenMP thread at a time.  Per-row calls from many
+// host threads serialise inside the CUDA driver; here a batch of rows is three launches in total:
+//   1. rbergomi_rows_kernel   all rows' paths (blockIdx.y = row, per-row model / step count / tables)
+//   2. rows_price_kernel      one CTA per row runs Asymptotic, Branching, LSM and Martingale out of shared memory
+//                             (small_bodies.cuh -- the same device routines the per-row API uses for small path sets)
+// Rows are independent: a multi-GPU run gives each rank a slice of the rows, no collective.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "small_bodies.cuh"
+
+namespace {
+
+struct RowDev {
+    int64_t slab_off;
+    int n_steps, is_call;
+    double K, r, dt, maturity, disc, sigma, dividend;
+};
+
+template <int P>
+__global__ void __launch_bounds__(SB_NT, 1) rows_price_kernel(const RowDev* __restrict__ rows, const float* __restrict__ slabs, int64_t ld, int n, int n_br,
+                                                             int max_iter, PhiloxKeys keys, uint64_t path_offset, double* __restrict__ out /*[rows][8]*/) {
+    extern __shared__ double sm[];
+    __shared__ double res[4];
+    const RowDev R = rows[blockIdx.x];
+    double* o = out + (size_t)blockIdx.x * 8;
+    const int M = R.n_steps + 1;
+    if (R.n_steps < 1) {  // PredictionGen.cpp:720-733: such rows are skipped and written as zeros
+        if (threadIdx.x < 8) o[threadIdx.x] = 0.0;
+        return;
+    }
+    const float* S = slabs + R.slab_off;
+    // Asymptotic (PredictionGen.cpp:788)
+    sb_asymptotic<float>(S, ld, n, M, R.K, R.is_call, R.r, R.dt, R.maturity, R.sigma, R.dividend, sm, res);
+    if (threadIdx.x == 0) o[0] = res[1] > 0.0 ? res[0] / res[1] : 0.0;
+    __syncthreads();
+    // Branching, exercise dates 0 .. steps-1 (:780-783, :789)
+    {
+        int kend = M;
+        for (int j = 0; j < M; ++j)
+            if ((double)j * R.dt > R.maturity) { kend = j; break; }
+        const int n_ex = R.n_steps < kend ? R.n_steps : kend;  // dates visited before the first t > maturity
+        if (n_ex > 0) {
+            const int j_hi = kend - 1 > n_ex - 1 ? kend - 1 : n_ex - 1;
+            sb_branching<float>(S, ld, n, j_hi, 0, kend, R.n_steps - 1, nullptr, nullptr, n_ex, R.r, R.dt, R.K, R.is_call, n_br, keys,
+                                path_offset + (uint64_t)blockIdx.x * (uint64_t)n, nullptr, sm, sm + n, res);
+            if (threadIdx.x == 0) o[1] = 0.5 * (res[0] / (double)n + res[1] / (double)n);
+        } else if (threadIdx.x == 0) {
+            o[1] = 0.0;
+        }
+        __syncthreads();
+    }
+    // LSM (:790)
+    sb_lsm<float, P>(S, ld, n, M, R.K, R.is_call, R.disc, R.dt, R.maturity, sm, nullptr, nullptr, nullptr, nullptr, nullptr, res);
+    if (threadIdx.x == 0) {
+        o[2] = res[0] / res[2];
+        const double var = res[2] > 1.0 ? res[1] / (res[2] - 1.0) : 0.0;
+        o[4] = var > 0.0 ? sqrt(var / res[2]) : 0.0;
+    }
+    __syncthreads();
+    // Martingale (:791)
+    sb_martingale<float, P>(S, ld, n, M, R.K, R.is_call, R.r, R.dt, R.maturity, max_iter, sm, sm + 4 * (size_t)n, res);
+    if (threadIdx.x == 0) o[3] = 0.5 * (res[0] / (double)n + res[1] / (double)n);
+}
+
+typedef void (*RowsFn)(const RowDev*, const float*, int64_t, int, int, int, PhiloxKeys, uint64_t, double*);
+RowsFn pick_rows(int p) {
+    switch (p) {
+        case 0: return rows_price_kernel<0>;
+        case 1: return rows_price_kernel<1>;
+        case 2: return rows_price_kernel<2>;
+        case 3: return rows_price_kernel<3>;
+        case 4: return rows_price_kernel<4>;
+        case 5: return rows_price_kernel<5>;
+        default: return rows_price_kernel<6>;
+    }
+}
+
+}  // namespace
+
+extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int n_paths, int poly_order, int num_branches, int max_iterations,
+                              uint64_t seed, uint64_t path_offset, mcp_row_result* out, float* gen_ms, float* price_ms) {
+    if (!ctx || !rows || !out) return MCP_ERR_INVALID;
+    if (n_rows <= 0) return MCP_OK;
+    if (n_paths < 1 || n_paths > SB_MAX_PATHS) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: n_paths %d outside [1, %d]", n_paths, SB_MAX_PATHS);
+    if (poly_order < 0 || poly_order > MAXP) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: poly_order %d outside [0, %d]", poly_order, MAXP);
+    if (num_branches <= 0) return mcp_fail(ctx, MCP_ERR_INVALID, "rows: numBranches must be positive");
+    if (max_iterations <= 0) return mcp_fail(ctx, MCP_ERR_DOMAIN, "MartingaleOptimization: maxIterations must be positive.");
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int max_steps = 1;
+    for (int r = 0; r < n_rows; ++r) {
+        if (rows[r].n_steps > 512) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: row %d has %d steps (> 512)", r, rows[r].n_steps);
+        if (rows[r].n_steps >= 1 && !(rows[r].sigma > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "AsymptoticAnalysis: Volatility must be positive.");
+        if (rows[r].n_steps >= 1 && !(rows[r].strike > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "BranchingProcesses: Strike must be positive.");
+        if (rows[r].n_steps > max_steps) max_steps = rows[r].n_steps;
+    }
+    const int64_t ld = mcp_round_up(n_paths, 128);
+    const int64_t slab_stride = (int64_t)(max_steps + 1) * ld;
+    // rows per chunk: at most ~2 GiB of slabs at a time
+    int64_t chunk = ((int64_t)2 << 30) / (slab_stride * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_rows) chunk = n_rows;
+    const size_t smem = (4 * (size_t)n_paths + (size_t)(max_steps + 1) * 2 + 8) * sizeof(double);
+    if (smem > 200 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: %d paths x %d steps does not fit one CTA", n_paths, max_steps);
+    RowsFn fn = pick_rows(poly_order);
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, SB_NT, smem, nullptr));
+    MCP_TRY(mcp_carry_reserve(ctx, (size_t)chunk * slab_stride * 4 + (size_t)chunk * (sizeof(RowDev) + 64) + 4096));
+    float* d_slabs = (float*)ctx->carry;
+    RowDev* d_rows = (RowDev*)((unsigned char*)ctx->carry + (size_t)chunk * slab_stride * 4);
+    double* d_out = (double*)((unsigned char*)d_rows + mcp_round_up((int64_t)(chunk * sizeof(RowDev)), 256));
+    const PhiloxKeys keys = philox_make_keys(seed ^ 0x5bd1e995ull);  // resampling stream of the Branching pricer
+    cudaEvent_t e0, e1, e2;
+    MCP_CUDA(ctx, cudaEventCreate(&e0));
+    MCP_CUDA(ctx, cudaEventCreate(&e1));
+    MCP_CUDA(ctx, cudaEventCreate(&e2));
+    float g_total = 0.f, p_total = 0.f;
+    int rc = MCP_OK;
+    std::vector<RowDev> h_rows((size_t)chunk);
+    std::vector<int> steps((size_t)chunk);
+    std::vector<double> h_out((size_t)chunk * 8);
+    for (int64_t r0 = 0; r0 < n_rows && rc == MCP_OK; r0 += chunk) {
+        const int nr = (int)(n_rows - r0 < chunk ? n_rows - r0 : chunk);
+        for (int k = 0; k < nr; ++k) {
+            const mcp_row& R = rows[r0 + k];
+            RowDev& D = h_rows[(size_t)k];
+            D.slab_off = (int64_t)k * slab_stride;
+            D.n_steps = R.n_steps;
+            D.is_call = R.is_call;
+            D.K = R.strike; D.r = R.r; D.dt = R.dt; D.maturity = R.maturity; D.sigma = R.sigma; D.dividend = R.dividend;
+            D.disc = exp(-R.r * R.dt);
+            steps[(size_t)k] = R.n_steps;
+        }
+        cudaEventRecord(e0, ctx->stream);
+        rc = mcp_rows_generate(ctx, &rows[r0].model, sizeof(mcp_row), steps.data(), nr, n_paths, seed, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_slabs,
+                               slab_stride, ld);
+        if (rc != MCP_OK) break;
+        cudaEventRecord(e1, ctx->stream);
+        if (cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: H2D failed"); break; }
+        fn<<<nr, SB_NT, smem, ctx->stream>>>(d_rows, d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_out);
+        ctx->launches++;
+        cudaEventRecord(e2, ctx->stream);
+        if (cudaMemcpyAsync(h_out.data(), d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: pricing kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        for (int k = 0; k < nr; ++k) {
+            mcp_row_result& o = out[r0 + k];
+            o.asymptotic = h_out[(size_t)k * 8 + 0];
+            o.branching = h_out[(size_t)k * 8 + 1];
+            o.lsm = h_out[(size_t)k * 8 + 2];
+            o.martingale = h_out[(size_t)k * 8 + 3];
+            o.lsm_std_error = h_out[(size_t)k * 8 + 4];
+        }
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, e0, e1) == cudaSuccess) g_total += a;
+        if (cudaEventElapsedTime(&b, e1, e2) == cudaSuccess) p_total += b;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (gen_ms) *gen_ms = g_total;
+    if (price_ms) *price_ms = p_total;
+    return rc;
+}

@@ -210,6 +210,26 @@ class Engine:
             se.ctypes.data_as(capi._dp), C.byref(g), C.byref(l)))
         return px, se, g.value, l.value
 
+    def price_rows(self, rows, n_paths: int = 250, poly_order: int = 2, num_branches: int = 10, max_iterations: int = 5,
+                   seed: int = 0, path_offset: int = 0):
+        """Batched row driver (mcp_price_rows).  rows: iterable of dicts with keys model (dict of S0, r, xi, H, eta, rho,
+        dt), n_steps, is_call, r, strike, maturity, dt, sigma, dividend.  Returns (array [n_rows][5] = asymptotic,
+        branching, lsm, martingale, lsm_std_error; gen_ms; price_ms)."""
+        rows = list(rows)
+        arr = (capi.Row * max(len(rows), 1))()
+        for k, row in enumerate(rows):
+            md = row["model"]
+            arr[k].model = RbergomiParams(md["S0"], md["r"], md["xi"], md["H"], md["eta"], md["rho"], md["dt"])
+            arr[k].n_steps, arr[k].is_call = int(row["n_steps"]), int(bool(row["is_call"]))
+            arr[k].r, arr[k].strike, arr[k].maturity, arr[k].dt = row["r"], row["strike"], row["maturity"], row["dt"]
+            arr[k].sigma, arr[k].dividend = row["sigma"], row["dividend"]
+        res = (capi.RowResult * max(len(rows), 1))()
+        g, p = C.c_float(), C.c_float()
+        self._chk(self._L.mcp_price_rows(self._h, arr, len(rows), n_paths, poly_order, num_branches, max_iterations, seed,
+                                         path_offset, res, C.byref(g), C.byref(p)))
+        out = np.array([[x.asymptotic, x.branching, x.lsm, x.martingale, x.lsm_std_error] for x in res[:len(rows)]])
+        return out.reshape(len(rows), 5), g.value, p.value
+
     # -- the other three plugins (SURVEY 8f) ------------------------------------------------------
     def asymptotic_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, sigma, dividend) -> float:
         px = C.c_double()
