@@ -226,3 +226,24 @@ def test_lsm_single_launch_kernel_for_small_path_sets(engine, port, monkeypatch,
     assert big.n_kernel_launches > n
     assert abs(big.price - got.price) <= 1e-10 * max(1.0, abs(got.price))
     assert np.array_equal(big.first_exercise, got.first_exercise)
+
+
+def test_config3_full_size_properties(engine):
+    """BASELINE config 3 at its full single-GPU size (2^26 paths x 252 steps, cubic basis, 67.9 GB slab) through
+    size-independent properties: determinism (same seed, same bits), agreement within 3 standard errors with an
+    independent 2^22-path price of the same estimator, standard error shrinking like 1/sqrt(N), the American put above
+    its European value on the same paths' law, and the global path count."""
+    free = engine.device_info()["free_bytes"]
+    if free < 90e9:
+        pytest.skip("needs ~70 GB of free HBM")
+    model = dict(S0=100.0, r=0.05, xi=0.04, H=0.1, eta=1.9, rho=-0.9, dt=1 / 252)
+    lsm = dict(r=0.05, strike=100.0, maturity=1.0, dt=1 / 252, is_call=False, poly_order=3, carry=m.MCP_F32)
+    big, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 26, 252, seed=3)
+    again, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 26, 252, seed=3)
+    assert big.price == again.price and big.std_error == again.std_error and big.n_paths_global == 1 << 26
+    small, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 22, 252, seed=4)
+    assert abs(big.price - small.price) < 3 * np.hypot(big.std_error, small.std_error), (big.price, small.price)
+    assert big.std_error == pytest.approx(small.std_error / 4.0, rel=0.02)  # 16x the paths
+    euro = dict(lsm, maturity=0.0)  # every step past "maturity" is discount-only: the European value of the terminal payoff
+    eu, _ = engine.price_rbergomi_lsm(model, euro, 1 << 22, 252, seed=4)
+    assert small.price > eu.price > 0.0

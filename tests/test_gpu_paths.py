@@ -147,3 +147,24 @@ def test_martingale_property_large(engine):
     assert abs(m - CFG2["S0"]) < 4 * se, (m, se)
     assert np.all(np.isfinite(tm)) and tm.min() > 0
     ps.close()
+
+
+def test_rbergomi_config2_full_size_one_million_injected_paths(engine, port):
+    """BASELINE config 2 at its full size: 2^20 paths x 252 steps, H=0.1, eta=1.9, rho=-0.9, every normal injected in
+    the reference's order (4.2 GB of fp32 draws, streamed in 64k-path chunks), all 253 columns against the oracle."""
+    n, chunk = 252, 1 << 16
+    worst, mean_sum = 0.0, 0.0
+    for c in range(16):
+        rng = np.random.default_rng(1000 + c)
+        d = f32_draws(rng, (chunk, 4 * n))
+        ps = engine.pathset(chunk, n)
+        engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], injected=d,
+                            path_offset=c * chunk)
+        got = ps.download()
+        ps.close()
+        want = port.rbergomi_paths(CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], n, d.astype(np.float64))
+        rel = np.abs(got - want) / np.abs(want)
+        worst = max(worst, float(rel.max()))
+        mean_sum += float(rel.mean())
+    assert worst < REL_TOL, f"max rel err over 2^20 paths {worst:.3e}"
+    assert mean_sum / 16 < 1e-6

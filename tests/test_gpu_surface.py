@@ -45,3 +45,20 @@ def test_surface_monotone_in_strike_and_rank_split_is_exact(engine):
         assert np.all(np.isnan(p[~own])) and not np.any(np.isnan(p[own]))
         merged[own] = p[own]
     np.testing.assert_array_equal(merged, full)       # zero-collective split: bit-identical to the single-rank surface
+
+
+def test_surface_config5_full_size(engine):
+    """BASELINE config 5 at full size on one GPU: 16 strikes (70..130) x 16 maturities (m/16 y), 2^22 paths per contract,
+    cubic basis, native Philox -- 256 American puts.  Size-independent properties: non-decreasing in strike (same paths
+    per maturity), the at-the-money put gains value with maturity, deep in-the-money puts are worth at least intrinsic."""
+    if engine.device_info()["free_bytes"] < 12e9:
+        pytest.skip("needs ~5 GB of free HBM")
+    strikes = np.arange(70.0, 131.0, 4.0)
+    mats = np.arange(1, 17) / 16.0
+    px, se, gen_ms, lsm_ms = engine.price_surface_rbergomi_lsm(MODEL, strikes, mats, 1 << 22, r=0.05, poly_order=3, seed=9)
+    assert px.shape == (16, 16) and np.all(np.isfinite(px))
+    assert np.all(np.diff(px, axis=1) >= 0)
+    atm = px[:, 8]  # K = 102
+    assert np.all(np.diff(atm) > -3 * np.hypot(se[1:, 8], se[:-1, 8]))
+    assert np.all(px[:, -1] >= 30.0 - 1e-6)
+    print(f"config 5 on one B200: generation {gen_ms:.0f} ms + LSM {lsm_ms:.0f} ms for 256 contracts x 2^22 paths")
