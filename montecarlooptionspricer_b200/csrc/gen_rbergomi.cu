@@ -547,6 +547,8 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_paths_n256_kernel(RbParams P, 
     }
 }
 
+#include "gen_rbergomi_x2.cuh"
+
 size_t smem_bytes(int Mp, int TP) {
     const int G = NT / TP;
     return (size_t)Mp * TP * 8 + (size_t)Mp * TP * 4 + (size_t)G * TP * 4 + (size_t)Mp * (8 + 8 + 4 + 4);
@@ -719,8 +721,27 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         }
     };
 
-    const bool n256 = (Mp == 256 && TP == 32 && !getenv("MCP_GEN_GENERIC"));
-    if (n256) {
+    // 256-point transforms (128 < n <= 256 steps): specialised kernels.  MCP_GEN_IMPL = 2 (default): two paths per thread,
+    // packed fp32x2 math; 1: one path per thread; 0: the generic kernel.
+    const char* impl_env = getenv("MCP_GEN_IMPL");
+    const int impl = getenv("MCP_GEN_GENERIC") ? 0 : (impl_env && *impl_env ? atoi(impl_env) : 2);
+    if (Mp == 256 && TP == 32 && impl == 2) {
+        run = [&](const RbParams& Q, const float* din, float* dout, float* out) -> int {
+            const bool inject = din != nullptr, dmp = dout != nullptr;
+            void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const float*, float*, float*);
+            if (inject) kern = dmp ? rbergomi_paths_n256x2_kernel<true, true> : rbergomi_paths_n256x2_kernel<true, false>;
+            else kern = dmp ? rbergomi_paths_n256x2_kernel<false, true> : rbergomi_paths_n256x2_kernel<false, false>;
+            int occ = 0;
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)kern, NT2, X2_SMEM, &occ));
+            if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n256x2 kernel does not fit");
+            const int64_t n_tiles = (Q.n_paths + 31) / 32;
+            int64_t grid = (int64_t)ctx->sm_count * occ;
+            if (grid > n_tiles) grid = n_tiles;
+            kern<<<(unsigned)grid, NT2, X2_SMEM, ctx->stream>>>(Q, K, d_phis, d_tw, d_comp2, din, dout, out);
+            MCP_LAUNCH_CHECK(ctx);
+            return MCP_OK;
+        };
+    } else if (Mp == 256 && TP == 32 && impl == 1) {
         run = [&](const RbParams& Q, const float* din, float* dout, float* out) -> int {
             const bool inject = din != nullptr, dmp = dout != nullptr;
             void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const float*, float*, float*);
