@@ -357,6 +357,7 @@ struct KernelKey {
 };
 std::mutex g_kernel_mu;
 std::map<KernelKey, int> g_kernel_occ;
+std::map<std::pair<int, const void*>, size_t> g_kernel_smem_limit;  // dynamic shared-memory limit already granted (only ever raised)
 }  // namespace
 
 int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, int* occ_out) {
@@ -369,7 +370,14 @@ int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, 
             return MCP_OK;
         }
     }
-    if (smem > 48 * 1024) MCP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lk(g_kernel_mu);
+        size_t& granted = g_kernel_smem_limit[std::make_pair(ctx->device, kernel)];
+        if (smem > granted) {
+            MCP_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            granted = smem;
+        }
+    }
     int occ = 0;
     MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
     {

@@ -22,7 +22,10 @@ def make_rows(rng, n_rows):
     return rows
 
 
-def test_batched_rows_equal_per_row_calls_and_oracle(engine, port):
+def test_batched_rows_equal_per_row_calls_and_oracle(engine, port, monkeypatch):
+    # the batch generates with the generic kernel (rows differ in length); pin the per-row calls to the same kernel so that
+    # both sides see bit-identical paths (the specialised 256-point kernels agree with it to fp32 rounding only)
+    monkeypatch.setenv("MCP_GEN_IMPL", "0")
     rng = np.random.default_rng(12)
     rows = make_rows(rng, 14)
     n_paths, seed = 250, 77
