@@ -266,13 +266,13 @@ def main():
     # physical DRAM bytes per launch from the committed `ncu --set full` captures (profiles/r01g_summary.md, 2^26 paths):
     # they scale with the path count, so they are reported per path-step and multiplied out here
     NCU_SWEEP_BYTES_PER_PATH = (805.39e6 + 219.95e6) / (1 << 26)            # S_j + S_{j-1} + V read, V written back
-    NCU_GEN_BYTES_PER_PATHSTEP = (70.55e9 + 0.022e9) / ((1 << 26) * 253.0)  # the slab, written once
+    NCU_GEN_BYTES_PER_PATHSTEP = (67.86e9 + 0.02e9) / ((1 << 26) * 253.0)   # the slab, written once (profiles/r01j_summary.md)
     kernels = {
         "rbergomi_paths_kernel": {"bound": "issue slots (FP32/INT + SFU); reported vs its HBM store because the contract asks for it",
                                   "launches_per_step": 1, "ms": prof["gen_kernel_ms"],
                                   "algorithmic_bytes": GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1), "achieved_gbs": gen_gbs,
                                   "frac_hbm": gen_gbs / peak, "traffic": NCU_GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1),
-                                  "instructions_per_path_step": 110.5, "issue_slot_utilisation": 0.62},
+                                  "instructions_per_path_step": 86, "issue_slot_utilisation": 0.52, "fma_heavy_pipe": 0.57, "xu_pipe": 0.39},
         "lsm_sweep_kernel": {"bound": "hbm", "launches_per_step": prof["n_sweep_launches"], "avg_ms": sweep_avg_ms,
                              "total_ms": prof["sweep_kernels_ms"], "algorithmic_bytes_per_launch": lsm_bytes * n_loc,
                              "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak,
@@ -287,8 +287,8 @@ def main():
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dk["achieved_gbs"] / peak, "traffic": dk["traffic"], "peak_source": peak_src,
-                "note": "generator: ~110 issued instructions per path-step vs 4 B stored => issue-bound (ncu: issue slots 62%, XU/SFU 41%, FMA 42%, "
-                        "ALU 34%, DRAM 11%; profiles/r01g_summary.md); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
+                "note": "generator: 86 issued instructions per path-step vs 4 B stored => bound by issue slots and the FMA-heavy pipe (ncu: issue "
+                        "slots 52%, FMA-heavy 57% (Philox IMAD.WIDE + packed fp32x2), XU/SFU 39%, ALU 35%, DRAM 11%; profiles/r01j_summary.md); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
                         "algorithmic 12 B/path, physical traffic 16 B/path (S_{j-1} is read again as the next launch's S_j)",
                 "step_share": {"rbergomi_paths_kernel": prof["gen_kernel_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"]),
                                "lsm_sweep_kernel": prof["sweep_kernels_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"])},
