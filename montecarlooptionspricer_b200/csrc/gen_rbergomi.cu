@@ -13,9 +13,11 @@
 //     global store is one full 128 B line of consecutive paths at one time index (time-major slab);
 //   * normals come from Philox4x32-10 keyed by (global path id, step): one call = the four normals a
 //     path-step consumes (Zre, Zim, W1, W2) -- nothing is carried between steps or paths;
-//   * the M'-point complex DFT runs in shared memory as radix-8 (+ one radix-4/2) decimation-in-frequency
+//   * the M'-point complex DFT runs in shared memory as radix-16 (+ one radix-8/4/2) decimation-in-frequency
 //     passes; output is left digit-reversed and read back through a position table, so there is no
 //     reordering pass.  sqrt(2H) eta / M' and log2(e) are folded into the phi table on the host;
+//   * the benchmark shape (128 < n <= 256 steps) has its own kernel with two paths per thread and packed fp32x2
+//     arithmetic over the pair (gen_rbergomi_x2.cuh); this file's kernel is the generic one (any n <= 4096);
 //   * the price recursion is a log-space prefix sum: per-thread serial chunk + one cross-chunk offset, then
 //     S = S0 exp2(.).  fp32 throughout: measured |rel err| vs the fp64 oracle ~3e-7 (tolerance 1e-5).
 #include <math.h>
@@ -395,158 +397,6 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_rows_kernel(const RbRow* __res
     rbergomi_tiles<32, false, false>(R.P, K, phis, tw, comp2, rev, nullptr, nullptr, slabs + R.slab_off, blockIdx.x, gridDim.x);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// The benchmark shape, fully specialised: 128 < n <= 256 steps (M' = 256 = 16 x 16), 32-path tiles, 16 warps.
-// Everything the generic kernel computes at run time is a compile-time constant here, so every shared-memory
-// access is `base + immediate`:
-//   warp g owns time chunk [16g, 16g+16) in phases 1 and 3;
-//   DIF pass 1: warp j transforms column j (elements j + 16q) and scales output s by w256^{js} (table tw2[j][s]);
-//   DIF pass 2: warp g transforms its own chunk; output s is X_m with m = g + 16 s (no digit-reversal table).
-// Shared memory: float2 A[256][32] | float W[256][32] | float tot[16][32] | float2 phis[256] | float2 tw2[16][16] | float comp2[256]
-// ---------------------------------------------------------------------------------------------------------
-constexpr int N256_SMEM = 256 * 32 * 8 + 256 * 32 * 4 + 16 * 32 * 4 + 256 * 8 + 256 * 8 + 256 * 4;
-
-template <bool INJECT, bool DUMP>
-__global__ void __launch_bounds__(NT, 2) rbergomi_paths_n256_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
-                                                                   const float2* __restrict__ g_tw, const float* __restrict__ g_comp2,
-                                                                   const float* __restrict__ draws_in, float* __restrict__ draws_out,
-                                                                   float* __restrict__ out) {
-    constexpr int TP = 32, MP = 256;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* A = reinterpret_cast<float2*>(smem_raw);
-    float* W = reinterpret_cast<float*>(A + MP * TP);
-    float* tot = W + MP * TP;
-    float2* phis = reinterpret_cast<float2*>(tot + 16 * TP);
-    float2* tw2 = phis + MP;
-    float* comp2 = reinterpret_cast<float*>(tw2 + MP);
-    const int n = P.n;
-    const int tid = threadIdx.x, p = tid & 31, g = tid >> 5;
-    if (tid < MP) {
-        phis[tid] = tid < n ? g_phis[tid] : make_float2(0.f, 0.f);
-        tw2[tid] = g_tw[((tid >> 4) * (tid & 15)) & (MP - 1)];  // w256^{j s}, j = tid / 16, s = tid % 16
-        comp2[tid] = tid < n ? g_comp2[tid] : 0.f;
-    }
-    const int k0 = g * 16;
-    const bool full = k0 + 16 <= n;  // warp-uniform: only the last chunk can be ragged
-    const int64_t n_tiles = (P.n_paths + TP - 1) / TP;
-    float2* const Ac = A + k0 * TP + p;  // this thread's chunk
-    float* const Wc = W + k0 * TP + p;
-    const float2* const phc = phis + k0;
-    __syncthreads();
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t path = tile * TP + p;
-        const bool live = path < P.n_paths;
-        const uint64_t gid = P.path_offset + (uint64_t)path;
-        const uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32);
-
-        // ---- phase 1: normals -> A = phis (.) Z, W = dW -----------------------------------------------------
-#pragma unroll 1
-        for (int kq = 0; kq < 16; kq += 4) {
-            float z[8], w[4];
-            if (INJECT) {
-                const int64_t col = live ? path : 0;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int k = k0 + kq + t;
-                    const bool in = k < n;
-                    z[2 * t] = in ? draws_in[(int64_t)(2 * k) * P.ld_draws + col] : 0.f;
-                    z[2 * t + 1] = in ? draws_in[(int64_t)(2 * k + 1) * P.ld_draws + col] : 0.f;
-                    w[t] = in ? P.rho * draws_in[(int64_t)(2 * n + k) * P.ld_draws + col] + P.rho_c * draws_in[(int64_t)(3 * n + k) * P.ld_draws + col]
-                              : 0.f;  // RoughVolatility.cpp:356-358
-                }
-            } else {
-                const int kk = k0 + kq;
-                const uint4 xa = philox4x32_10(c0, c1, (uint32_t)(kk >> 1), 0u, K);
-                const uint4 xb = philox4x32_10(c0, c1, (uint32_t)(kk >> 1) + 1u, 0u, K);
-                const uint4 xw = philox4x32_10(c0, c1, (uint32_t)(kk >> 2), 2u, K);
-                box_muller(xa.x, xa.y, z[0], z[1]);
-                box_muller(xa.z, xa.w, z[2], z[3]);
-                box_muller(xb.x, xb.y, z[4], z[5]);
-                box_muller(xb.z, xb.w, z[6], z[7]);
-                box_muller(xw.x, xw.y, w[0], w[1]);
-                box_muller(xw.z, xw.w, w[2], w[3]);
-                if (DUMP && live) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int k = kk + t;
-                        if (k < n) {
-                            draws_out[(int64_t)(2 * k) * P.ld_draws + path] = z[2 * t];
-                            draws_out[(int64_t)(2 * k + 1) * P.ld_draws + path] = z[2 * t + 1];
-                            draws_out[(int64_t)(2 * n + k) * P.ld_draws + path] = P.rho * w[t];
-                            draws_out[(int64_t)(3 * n + k) * P.ld_draws + path] = P.rho_c * w[t];
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const bool in = full || (k0 + kq + t < n);
-                Ac[(kq + t) * TP] = in ? cmul(phc[kq + t], make_float2(z[2 * t], z[2 * t + 1])) : make_float2(0.f, 0.f);
-                Wc[(kq + t) * TP] = in ? w[t] : 0.f;
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2a: DIF pass 1 on column g ---------------------------------------------------------------
-        {
-            float2* a = A + g * TP + p;
-            float2 x[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) x[q] = a[q * 16 * TP];
-            dft16_transposed(x);
-            const float2* t2 = tw2 + g * 16;
-#pragma unroll
-            for (int sx = 1; sx < 16; ++sx) x[out_slot<16>(sx)] = cmul(x[out_slot<16>(sx)], t2[sx]);
-#pragma unroll
-            for (int sx = 0; sx < 16; ++sx) a[sx * 16 * TP] = x[out_slot<16>(sx)];
-        }
-        __syncthreads();
-
-        // ---- phase 2b: DIF pass 2 on chunk g; output s is X_m, m = g + 16 s -> log2-increment written over dW_m ----
-        {
-            float2 x[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) x[q] = Ac[q * TP];
-            dft16_transposed(x);
-            float* wm = W + g * TP + p;
-            const float* cm = comp2 + g;
-#pragma unroll
-            for (int sx = 0; sx < 16; ++sx) {
-                if (sx < 15 || g + 240 < n) wm[sx * 16 * TP] = log2_increment(x[out_slot<16>(sx)].x + cm[sx * 16], wm[sx * 16 * TP], P);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 3: log2-space prefix sum over time, S = S0 2^(.) -------------------------------------------
-        {
-            float c[16];
-#pragma unroll
-            for (int t = 0; t < 16; ++t) c[t] = Wc[t * TP];  // rows >= n hold 0
-#pragma unroll
-            for (int t = 1; t < 16; ++t) c[t] += c[t - 1];
-            tot[g * TP + p] = c[15];
-            __syncthreads();
-            float off = 0.f;
-            for (int gg = 0; gg < g; ++gg) off += tot[gg * TP + p];
-            if (live) {
-                if (g == 0) out[path] = P.S0;
-                float* o = out + (int64_t)(k0 + 1) * P.ld + path;
-                if (full) {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t, o += P.ld) *o = P.S0 * fast_ex2(off + c[t]);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t, o += P.ld)
-                        if (k0 + t < n) *o = P.S0 * fast_ex2(off + c[t]);
-                }
-            }
-        }
-        // no barrier needed here: the next tile's phase 1 writes A / W chunk g only (read by this thread alone in
-        // phase 3) and `tot` is rewritten only after the next three barriers
-    }
-}
-
 #include "gen_rbergomi_x2.cuh"
 
 size_t smem_bytes(int Mp, int TP) {
@@ -721,8 +571,8 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         }
     };
 
-    // 256-point transforms (128 < n <= 256 steps): specialised kernels.  MCP_GEN_IMPL = 2 (default): two paths per thread,
-    // packed fp32x2 math; 1: one path per thread; 0: the generic kernel.
+    // 256-point transforms (128 < n <= 256 steps) run the specialised two-paths-per-thread kernel (gen_rbergomi_x2.cuh);
+    // MCP_GEN_IMPL=0 forces the generic kernel (used by tests that need bit-identical paths from both).
     const char* impl_env = getenv("MCP_GEN_IMPL");
     const int impl = getenv("MCP_GEN_GENERIC") ? 0 : (impl_env && *impl_env ? atoi(impl_env) : 2);
     if (Mp == 256 && TP == 32 && impl == 2) {
@@ -738,22 +588,6 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
             int64_t grid = (int64_t)ctx->sm_count * occ;
             if (grid > n_tiles) grid = n_tiles;
             kern<<<(unsigned)grid, NT2, X2_SMEM, ctx->stream>>>(Q, K, d_phis, d_tw, d_comp2, din, dout, out);
-            MCP_LAUNCH_CHECK(ctx);
-            return MCP_OK;
-        };
-    } else if (Mp == 256 && TP == 32 && impl == 1) {
-        run = [&](const RbParams& Q, const float* din, float* dout, float* out) -> int {
-            const bool inject = din != nullptr, dmp = dout != nullptr;
-            void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const float*, float*, float*);
-            if (inject) kern = dmp ? rbergomi_paths_n256_kernel<true, true> : rbergomi_paths_n256_kernel<true, false>;
-            else kern = dmp ? rbergomi_paths_n256_kernel<false, true> : rbergomi_paths_n256_kernel<false, false>;
-            int occ = 0;
-            MCP_TRY(mcp_kernel_config(ctx, (const void*)kern, NT, N256_SMEM, &occ));
-            if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n256 kernel does not fit");
-            const int64_t n_tiles = (Q.n_paths + 31) / 32;
-            int64_t grid = (int64_t)ctx->sm_count * occ;
-            if (grid > n_tiles) grid = n_tiles;
-            kern<<<(unsigned)grid, NT, N256_SMEM, ctx->stream>>>(Q, K, d_phis, d_tw, d_comp2, din, dout, out);
             MCP_LAUNCH_CHECK(ctx);
             return MCP_OK;
         };

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256x2_kernel(RbParams 
                 }
             }
         }
-        // no barrier needed here (see rbergomi_paths_n256_kernel): chunk g of re / im / W is private to this thread
-        // between the last barrier and the next tile's first one, and `tot` is rewritten three barriers later
+        // no barrier needed here: the next tile's phase 1 writes only chunk g of re / im / W (read by this thread alone in
+        // phase 3), and `tot` is rewritten only after the next three barriers
     }
 }

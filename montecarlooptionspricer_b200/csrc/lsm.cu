@@ -71,8 +71,6 @@ struct SweepArgs {
     int do_moments;  // accumulate moments of step j-1
     int do_final;    // j == 0: accumulate sum V0
     int solve_here;  // single GPU: the last CTA to finish also solves step j-1 (no extra launches)
-    int64_t pin_paths;  // leading paths whose carry lines are kept L2-resident across sweeps
-    int pin_mode;       // 1: evict_last hints, 2: plain accesses under a persisting access-policy window
     McpXchg x;          // peer-memory mailboxes (multi-GPU): the moment all-reduce happens inside this kernel
     unsigned long long seq;  // sequence number of this launch's exchange
     int l2_resident;    // two slab rows + the carry fit in L2: keep them there instead of streaming
@@ -211,119 +209,19 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_kernel(SweepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// sweep(j), THROUGHPUT kernel (fp32 slab + fp32 carry): all per-path arithmetic in fp32, only the cross-path
-// accumulation in fp64 (per-thread fp32 partial sums over <= 64 paths are folded into fp64 accumulators).
-// The kernel is then a pure HBM stream: 16 B/path of traffic (S_j, S_{j-1}, V in, V out), ~45 FP32 ops.
-// The discount is applied as a two-float product (d_hi + d_lo) so that 252 chained roundings stay unbiased;
-// the strike is split the same way.  Prices agree with the fp64 oracle to ~1e-7 relative (tolerance 1e-5);
-// exercise indices may differ from it at near-ties only (use the parity kernel when they must not).
-// ---------------------------------------------------------------------------------------------------------
-template <int P>
-__global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast_kernel(SweepArgs a) {
-    constexpr int NM = 3 * P + 2;
-    constexpr int NV = NM > 2 ? NM : 2;
-    constexpr int FLUSH = 8;  // iterations (x8 paths) between fp32 -> fp64 folds
-    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
-    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
-    float* __restrict__ V = reinterpret_cast<float*>(a.V);
-
-    const int mode = a.terminal ? 2 : a.d.kind[a.j];
-    float c[P + 1];
-#pragma unroll
-    for (int k = 0; k <= P; ++k) c[k] = (float)a.d.coef[(int64_t)a.j * COEF_LD + k];
-    const float mu = (float)a.d.mu[a.j], inv_s = (float)a.d.inv_s[a.j];
-    const float mu_p = (float)a.d.mu[a.j > 0 ? a.j - 1 : 0], inv_s_p = (float)a.d.inv_s[a.j > 0 ? a.j - 1 : 0];
-    const float K_hi = (float)a.K, K_lo = (float)(a.K - (double)K_hi);
-    const float d_hi = (float)a.disc, d_lo = (float)(a.disc - (double)d_hi);
-    const float sgn = a.is_call ? 1.f : -1.f;
-
-    double acc[NV];
-    float la[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) { acc[k] = 0.0; la[k] = 0.f; }
-    int since = 0;
-
-    const int64_t nvec = (a.n + 3) >> 2, npair = (nvec + 1) >> 1, pstride = (int64_t)gridDim.x * LSM_NT;
-    for (int64_t ip = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; ip < npair; ip += pstride) {
-        // two 4-wide vectors per iteration: 6 independent 16 B loads in flight per thread
-        const int64_t q = (a.j & 1) ? (npair - 1 - ip) : ip;
-        const int64_t i0 = q * 8, i1 = i0 + 4;
-        const bool has1 = i1 < a.n;
-        float4 s0 = *reinterpret_cast<const float4*>(Sj + i0), s1 = has1 ? *reinterpret_cast<const float4*>(Sj + i1) : s0;
-        float4 p0 = s0, p1 = s0, v0 = s0, v1 = s0;
-        if (a.do_moments) { p0 = *reinterpret_cast<const float4*>(Sp + i0); if (has1) p1 = *reinterpret_cast<const float4*>(Sp + i1); }
-        if (mode != 2) { v0 = *reinterpret_cast<const float4*>(V + i0); if (has1) v1 = *reinterpret_cast<const float4*>(V + i1); }
-        float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        float sp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const int nvalid = (int)(a.n - i0 < 8 ? a.n - i0 : 8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float pay = fmaxf(sgn * ((s[e] - K_hi) - K_lo), 0.f);  // include/core/common.h:8-14
-            if (mode == 2) {
-                v[e] = pay;
-            } else {
-                const float vd = fmaf(v[e], d_lo, v[e] * d_hi);
-                if (mode == 1) {
-                    v[e] = vd;
-                } else {
-                    const float x = (s[e] - mu) * inv_s;
-                    float cont = c[P];
-#pragma unroll
-                    for (int k = P - 1; k >= 0; --k) cont = fmaf(cont, x, c[k]);
-                    const bool itm = pay > 1e-14f, ex = !(pay < cont);
-                    v[e] = itm ? (ex ? pay : cont) : (pay < 1e-14f ? vd : 0.f);
-                    if (a.tau && itm && ex && e < nvalid) a.tau[i0 + e] = a.j;
-                }
-            }
-        }
-        *reinterpret_cast<float4*>(V + i0) = make_float4(v[0], v[1], v[2], v[3]);
-        if (has1) *reinterpret_cast<float4*>(V + i1) = make_float4(v[4], v[5], v[6], v[7]);
-        if (a.do_moments) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float payp = fmaxf(sgn * ((sp[e] - K_hi) - K_lo), 0.f);
-                if (e < nvalid && payp > 1e-14f) {
-                    const float x = (sp[e] - mu_p) * inv_s_p, y = fmaf(v[e], d_lo, v[e] * d_hi);
-                    float xp = x;
-                    la[0] += 1.f;
-                    la[2 * P + 1] += y;
-#pragma unroll
-                    for (int k = 1; k <= 2 * P; ++k) {
-                        la[k] += xp;
-                        if (k <= P) la[2 * P + 1 + k] = fmaf(xp, y, la[2 * P + 1 + k]);
-                        if (k < 2 * P) xp *= x;
-                    }
-                }
-            }
-        }
-        if (a.do_final) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (e < nvalid) la[0] += v[e];
-        }
-        if (++since == FLUSH) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) { acc[k] += (double)la[k]; la[k] = 0.f; }
-            since = 0;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] += (double)la[k];
-    if (a.do_moments || a.do_final) sweep_epilogue<NV, P>(a, acc);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// sweep(j), THROUGHPUT kernel v2: same arithmetic as lsm_sweep_fast_kernel, restructured for Blackwell.
-//   * packed fp32x2 math (FFMA2 / FADD2 / FMUL2, one issue slot per two paths): the v1 kernel issued ~77
-//     instructions per path and ran at 63% issue utilisation with DRAM only 56% busy -- it was as much
-//     instruction-bound as bandwidth-bound;
+// sweep(j), THROUGHPUT arithmetic (fp32 slab + fp32 carry), shared by the direct-load kernel below and the TMA-ring
+// kernel further down.  All per-path arithmetic in fp32, only the cross-path accumulation in fp64:
+//   * packed fp32x2 math (FFMA2 / FADD2 / FMUL2, one issue slot per two paths): the first scalar version issued ~77
+//     instructions per path and ran at 63% issue utilisation with DRAM only 56% busy -- as much instruction-bound as
+//     bandwidth-bound;
 //   * the in-the-money filter of the moments is a 0/1 multiplier on (x, y) instead of a divergent branch
 //     (x = 0 kills every power, y = 0 every cross moment);
-//   * the fp64 side of the accumulation lives in shared memory ([NV][256] doubles), not in 2 NV registers;
-//   * carry lines of the first `pin_paths` paths are accessed with an L2 evict_last policy so that they stay
-//     resident in the 126 MB L2 across all sweeps (each such line saves one HBM read AND one write-back per
-//     step); everything that is touched once per sweep is streamed (evict_first).
+//   * fp32 partial sums of <= 64 paths per lane are folded into fp64 accumulators that live in shared memory;
+//   * the discount is applied as a two-float product (d_hi + d_lo) so that 252 chained roundings stay unbiased; the
+//     strike is split the same way.  Prices agree with the fp64 oracle to ~1e-7 relative (tolerance 1e-5); exercise
+//     indices may differ from it at near-ties only (use the parity kernel when they must not).
+// L2 pinning of a carry prefix (evict_last hints, and a persisting access-policy window) was measured and gave nothing;
+// it is not in the code any more.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
 
@@ -351,10 +249,7 @@ struct F8 {
     }
 MCP_LD8(ld8_stream, ".L1::no_allocate.L2::evict_first")  // touched once per sweep
 MCP_LD8(ld8_keep, ".L1::no_allocate.L2::evict_normal")   // S_{j-1}: read again by the next sweep
-MCP_LD8(ld8_pinned, ".L1::no_allocate.L2::evict_last")   // carry lines meant to stay L2-resident across sweeps
 MCP_ST8(st8_stream, ".L2::evict_first")
-MCP_ST8(st8_pinned, ".L2::evict_last")
-MCP_ST8(st8_keep, ".L2::evict_normal")
 
 template <int P>
 struct FastConsts {
@@ -446,14 +341,12 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
 template <int P, bool TAU, bool TAIL>
 __device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts<P>& k, const float* __restrict__ Sj, const float* __restrict__ Sp,
                                             float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
-    const bool pinned = i0 < a.pin_paths;
     const F8 s8 = ld8_stream(Sj + i0);
     F8 p8 = s8, v8 = s8;
     if (a.do_moments) p8 = ld8_keep(Sp + i0);
-    if (mode != 2) v8 = pinned ? (a.pin_mode == 2 ? ld8_keep(V + i0) : ld8_pinned(V + i0)) : ld8_stream(V + i0);
+    if (mode != 2) v8 = ld8_stream(V + i0);
     fast2_compute<P, TAU, TAIL>(a, k, s8, p8, v8, i0, i0 + 4, mode, la);
-    if (pinned) { if (a.pin_mode == 2) st8_keep(V + i0, v8); else st8_pinned(V + i0, v8); }
-    else st8_stream(V + i0, v8);
+    st8_stream(V + i0, v8);
 }
 
 template <int P>
@@ -474,8 +367,8 @@ __device__ __forceinline__ void fast2_load_consts(const SweepArgs& a, FastConsts
     k.d_lo = splat2((float)(a.disc - (double)d_hi));
 }
 
-template <int P, bool TAU, int OCC>
-__global__ void __launch_bounds__(LSM_NT, OCC) lsm_sweep_fast2_kernel(SweepArgs a) {
+template <int P, bool TAU>
+__global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast2_kernel(SweepArgs a) {
     constexpr int NM = 3 * P + 2;
     constexpr int NV = NM > 2 ? NM : 2;
     constexpr int FLUSH = 8;  // groups (x8 paths) between fp32 -> fp64 folds
@@ -918,28 +811,16 @@ SweepFn pick_sweep(int p) {
     }
 }
 
-SweepFn pick_sweep_fast(int p) {
-    switch (p) {
-        case 0: return lsm_sweep_fast_kernel<0>;
-        case 1: return lsm_sweep_fast_kernel<1>;
-        case 2: return lsm_sweep_fast_kernel<2>;
-        case 3: return lsm_sweep_fast_kernel<3>;
-        case 4: return lsm_sweep_fast_kernel<4>;
-        case 5: return lsm_sweep_fast_kernel<5>;
-        default: return lsm_sweep_fast_kernel<6>;
-    }
-}
-
-template <bool TAU, int OCC>
+template <bool TAU>
 SweepFn pick_sweep_fast2(int p) {
     switch (p) {
-        case 0: return lsm_sweep_fast2_kernel<0, TAU, OCC>;
-        case 1: return lsm_sweep_fast2_kernel<1, TAU, OCC>;
-        case 2: return lsm_sweep_fast2_kernel<2, TAU, OCC>;
-        case 3: return lsm_sweep_fast2_kernel<3, TAU, OCC>;
-        case 4: return lsm_sweep_fast2_kernel<4, TAU, OCC>;
-        case 5: return lsm_sweep_fast2_kernel<5, TAU, OCC>;
-        default: return lsm_sweep_fast2_kernel<6, TAU, OCC>;
+        case 0: return lsm_sweep_fast2_kernel<0, TAU>;
+        case 1: return lsm_sweep_fast2_kernel<1, TAU>;
+        case 2: return lsm_sweep_fast2_kernel<2, TAU>;
+        case 3: return lsm_sweep_fast2_kernel<3, TAU>;
+        case 4: return lsm_sweep_fast2_kernel<4, TAU>;
+        case 5: return lsm_sweep_fast2_kernel<5, TAU>;
+        default: return lsm_sweep_fast2_kernel<6, TAU>;
     }
 }
 
@@ -962,9 +843,8 @@ int env_int(const char* name, int dflt) {
 }
 
 SweepFn pick_sweep(int slab_dtype, int carry_dtype, int p, bool want_tau) {
-    if (slab_dtype == MCP_F32 && carry_dtype == MCP_F32 && env_int("MCP_SWEEP_IMPL", 2) == 2)
-        return want_tau ? pick_sweep_fast2<true, 3>(p) : (env_int("MCP_SWEEP_OCC", 3) == 4 ? pick_sweep_fast2<false, 4>(p) : pick_sweep_fast2<false, 3>(p));
-    if (slab_dtype == MCP_F32) return carry_dtype == MCP_F32 ? pick_sweep_fast(p) : pick_sweep<float, double>(p);
+    if (slab_dtype == MCP_F32 && carry_dtype == MCP_F32) return want_tau ? pick_sweep_fast2<true>(p) : pick_sweep_fast2<false>(p);
+    if (slab_dtype == MCP_F32) return pick_sweep<float, double>(p);
     return carry_dtype == MCP_F32 ? pick_sweep<double, float>(p) : pick_sweep<double, double>(p);
 }
 
@@ -1105,32 +985,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     const bool p2p = multi && ctx->xchg.enabled;
     if (p2p) a.x = ctx->xchg;
     a.solve_here = (!multi || p2p) ? 1 : 0;
-    a.pin_paths = ((int64_t)env_int("MCP_SWEEP_PIN_MB", 0) << 20) / 4 / 8 * 8;  // carry bytes kept L2-resident
-    a.pin_mode = env_int("MCP_SWEEP_PIN_MODE", 1);
     a.l2_resident = ((size_t)N * 12 <= ((size_t)env_int("MCP_L2_RESIDENT_MB", 104) << 20)) ? 1 : 0;
-    if (a.pin_paths > N) a.pin_paths = N / 8 * 8;
-    bool window_set = false;
-    if (a.pin_paths > 0 && a.pin_mode == 2 && prm->carry == MCP_F32) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-        size_t want = (size_t)a.pin_paths * 4;
-        if (want > (size_t)max_persist) want = (size_t)max_persist;
-        if (want > (size_t)max_window) want = (size_t)max_window;
-        a.pin_paths = (int64_t)(want / 4 / 8 * 8);
-        if (getenv("MCP_DEBUG")) fprintf(stderr, "[mcp] persisting L2: max %d B, window max %d B, using %zu B\n", max_persist, max_window, want);
-        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = dV;
-            attr.accessPolicyWindow.num_bytes = want;
-            attr.accessPolicyWindow.hitRatio = 1.0f;
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-        }
-        cudaGetLastError();
-    }
     const int nm = 3 * p + 2;
     if (small) {
         SmallFn fn = ps->dtype == MCP_F32 ? pick_small<float>(p) : pick_small<double>(p);
@@ -1171,12 +1026,6 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
             lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD);
             MCP_LAUNCH_CHECK(ctx);
         }
-    }
-    if (window_set) {
-        cudaStreamAttrValue attr;
-        memset(&attr, 0, sizeof(attr));
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaCtxResetPersistingL2Cache();
     }
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
