@@ -19,6 +19,7 @@
  *   mcp_generate_stock_price_paths  GenerateStockPricePaths, exact call shape  src/core/PredictionGen.cpp:736-737
  *   mcp_price_surface_rbergomi_lsm  [new] the row loop of src/core/PredictionGen.cpp:542-866 for a strike x maturity grid
  *   mcp_price_rows              the whole per-row block of src/core/PredictionGen.cpp:700-791, batched over rows
+ *   mcp_gbm_nested_dual         [new] BASELINE config 4 (nested-simulation duality); no reference counterpart
  *   mcp_asymptotic_price        AsymptoticAnalysis::PredictOptionPrice      include/models/AsymptoticAnalysisPricer.h:8-15
  *   mcp_martingale_price        MartingaleOptimization::PredictOptionPrice  include/models/MartingaleOptimizationPricer.h:10-18
  *   mcp_branching_price         BranchingProcesses::PredictOptionPrice      include/models/BranchingProcessPricer.h:8-16
@@ -56,7 +57,8 @@ enum mcp_status {
 
 enum mcp_dtype { MCP_F32 = 0, MCP_F64 = 1 };       /* storage type of a path slab / of the LSM carry */
 enum mcp_basis { MCP_BASIS_MONOMIAL = 0,           /* 1, S, S^2 ... (LSMPricer.cpp:9-17) */
-                 MCP_BASIS_LAGUERRE = 1 };         /* L_0..L_p(S/K), unweighted: spans the same space */
+                 MCP_BASIS_LAGUERRE = 1,           /* L_0..L_p(S/K), unweighted: spans the same space */
+                 MCP_BASIS_STANDARDISED = 2 };     /* the device's own basis: rows [c_0..c_p, mu, 1/s], x = (S - mu) / s */
 
 /* ------------------------------------------------------------------------------------------- engine */
 int mcp_abi_version(void);
@@ -143,7 +145,7 @@ typedef struct mcp_lsm_result {
     int n_kernel_launches;
 } mcp_lsm_result;
 
-/* coeffs (nullable): host [n_steps][poly_order+1], row j = regression at step j in the requested basis,
+/* coeffs (nullable): host [n_steps][poly_order+1] ([poly_order+3] for MCP_BASIS_STANDARDISED), row j = regression at step j in the requested basis,
  *                    zeros where no path was in the money / past maturity;
  * first_exercise (nullable): host int32 [n_paths], tau_i = min{ j : exercised } else n_steps;
  * v0 (nullable): host double [n_paths], V[i][0]. */
@@ -161,6 +163,25 @@ int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_p
 int mcp_price_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *model, const mcp_lsm_params *lsm,
                            int64_t n_paths, int n_steps, uint64_t seed, uint64_t path_offset,
                            mcp_lsm_result *res, float *gen_ms);
+
+/* ------------------------------------------------- nested-simulation duality under GBM (config 4) [new]
+ * Andersen-Broadie upper bound for the Bermudan option with exercise dates j dt, j = 0..n_steps, under GBM:
+ *   1. exercise policy = the LSM regression fitted on n_policy_paths independent paths (seed ^ 1);
+ *   2. n_outer fresh paths (seed, path_offset + i): lower bound = mean discounted payoff of following the policy;
+ *   3. at every date of every outer path, n_inner inner paths continue from the outer state under the policy
+ *      (normals keyed by (outer id, date, inner id, step block)) -> continuation value Q_j; martingale
+ *      M_0 = 0, M_{j+1} = M_j + L_{j+1} - Q_j with L_j = policy value at j; upper = mean max_j (h_j - M_j), all discounted.
+ * The reference has no such algorithm (its MartingaleOptimization pricer is a polynomial fit), and its rough-vol
+ * driver is not adapted, so conditional inner simulation is only defined for the GBM model here: parity is unpinned by
+ * the reference; the test oracle is an independent restatement of this description. */
+typedef struct mcp_dual_result {
+    double lower, lower_se, upper, upper_se;
+    int64_t n_outer_global;
+    float policy_ms, outer_ms, nested_ms;
+} mcp_dual_result;
+int mcp_gbm_nested_dual(mcp_ctx *ctx, const mcp_gbm_params *model, double strike, int is_call, int n_steps,
+                        int poly_order, int64_t n_policy_paths, int64_t n_outer, int n_inner, uint64_t seed,
+                        uint64_t path_offset, mcp_dual_result *out);
 
 /* ---------------------------------------------------------------- batched strike x maturity surface (config 5)
  * prices[m][k] (row-major [n_maturities][n_strikes]) = LSM price of strike k at maturity m under the rough-vol model:

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libmcp_b200.so")
 MCP_OK, MCP_ERR_INVALID, MCP_ERR_CUDA, MCP_ERR_NCCL, MCP_ERR_NOMEM = 0, -1, -2, -3, -4
 MCP_ERR_EMPTY_PATHS, MCP_ERR_UNSUPPORTED, MCP_ERR_DOMAIN = -5, -6, -7
 MCP_F32, MCP_F64 = 0, 1
-MCP_BASIS_MONOMIAL, MCP_BASIS_LAGUERRE = 0, 1
+MCP_BASIS_MONOMIAL, MCP_BASIS_LAGUERRE, MCP_BASIS_STANDARDISED = 0, 1, 2
 
 
 class RbergomiParams(C.Structure):
@@ -41,6 +41,11 @@ class Row(C.Structure):
 class RowResult(C.Structure):
     _fields_ = [("asymptotic", C.c_double), ("branching", C.c_double), ("lsm", C.c_double), ("martingale", C.c_double),
                 ("lsm_std_error", C.c_double)]
+
+
+class DualResult(C.Structure):
+    _fields_ = [("lower", C.c_double), ("lower_se", C.c_double), ("upper", C.c_double), ("upper_se", C.c_double),
+                ("n_outer_global", C.c_int64), ("policy_ms", C.c_float), ("outer_ms", C.c_float), ("nested_ms", C.c_float)]
 
 
 class Profile(C.Structure):
@@ -90,6 +95,8 @@ SIGNATURES = {
                                          C.c_uint64, C.c_uint64, C.POINTER(LsmResult), _fp]),
     "mcp_price_surface_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), _dp, C.c_int, _dp, C.c_int,
                                                  C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _dp, _dp, _fp, _fp]),
+    "mcp_gbm_nested_dual": (C.c_int, [_vp, C.POINTER(GbmParams), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                      C.c_uint64, C.c_uint64, C.POINTER(DualResult)]),
     "mcp_price_rows": (C.c_int, [_vp, C.POINTER(Row), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                  C.POINTER(RowResult), _fp, _fp]),
     "mcp_estimate_rbergomi_params": (C.c_int, [_dp, C.c_int64, C.POINTER(RbergomiParams)]),

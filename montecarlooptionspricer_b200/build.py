@@ -22,7 +22,7 @@ PLUGINS = os.path.join(PKG, "libmcp_b200_plugins.so")
 DEMO = os.path.join(HOST, "plugin_rows_demo")
 LATENCY = os.path.join(HOST, "plugin_latency")
 
-CU_SOURCES = ["ctx.cu", "pathset.cu", "gen_rbergomi.cu", "gen_gbm.cu", "lsm.cu", "pricers.cu", "estimators.cu", "surface.cu", "rows.cu"]
+CU_SOURCES = ["ctx.cu", "pathset.cu", "gen_rbergomi.cu", "gen_gbm.cu", "lsm.cu", "pricers.cu", "estimators.cu", "surface.cu", "rows.cu", "dual.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",

@@ -1086,7 +1086,14 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         }
     }
     res->n_kernel_launches = (int)(ctx->launches - launches0);
-    if (coeffs) {
+    if (coeffs && prm->basis == MCP_BASIS_STANDARDISED) {  // rows [c_0 .. c_p, mu, 1/s]: cont(S) = sum_k c_k ((S - mu) / s)^k
+        for (int j = 0; j + 1 < M; ++j) {
+            double* out = coeffs + (size_t)j * (p + 3);
+            for (int k = 0; k <= p; ++k) out[k] = hcoef[(size_t)j * COEF_LD + k];
+            out[p + 1] = hmu[j];
+            out[p + 2] = his[j];
+        }
+    } else if (coeffs) {
         for (int j = 0; j + 1 < M; ++j) {
             double* out = coeffs + (size_t)j * (p + 1);
             bool any = false;

@@ -168,7 +168,7 @@ class Engine:
                   want_v0: bool = False) -> LsmOutput:
         prm = LsmParams(r, strike, maturity, dt, int(bool(is_call)), poly_order, basis, carry)
         res = LsmResult()
-        co = np.zeros((max(ps.n_steps, 1), poly_order + 1)) if want_coeffs else None
+        co = np.zeros((max(ps.n_steps, 1), poly_order + (3 if basis == capi.MCP_BASIS_STANDARDISED else 1))) if want_coeffs else None
         fe = np.zeros(ps.n_paths, dtype=np.int32) if want_first_exercise else None
         v0 = np.zeros(ps.n_paths) if want_v0 else None
         self._chk(self._L.mcp_lsm_price(
@@ -229,6 +229,15 @@ class Engine:
                                          path_offset, res, C.byref(g), C.byref(p)))
         out = np.array([[x.asymptotic, x.branching, x.lsm, x.martingale, x.lsm_std_error] for x in res[:len(rows)]])
         return out.reshape(len(rows), 5), g.value, p.value
+
+    def gbm_nested_dual(self, S0, r, sigma, dt, strike, is_call, n_steps, poly_order, n_policy_paths, n_outer, n_inner,
+                        seed: int = 0, path_offset: int = 0) -> dict:
+        """BASELINE config 4: Andersen-Broadie nested-simulation upper bound + policy lower bound under GBM."""
+        prm = GbmParams(S0, r, sigma, dt)
+        res = capi.DualResult()
+        self._chk(self._L.mcp_gbm_nested_dual(self._h, C.byref(prm), strike, int(bool(is_call)), n_steps, poly_order,
+                                              n_policy_paths, n_outer, n_inner, seed, path_offset, C.byref(res)))
+        return {k: getattr(res, k) for k, _ in capi.DualResult._fields_}
 
     # -- the other three plugins (SURVEY 8f) ------------------------------------------------------
     def asymptotic_price(self, ps: "PathSet", r, strike, maturity, dt, is_call, sigma, dividend) -> float:
