@@ -429,6 +429,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -468,7 +471,8 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     constexpr int FLUSH = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES);  // "stage filled" barriers (TMA completes them)
+    uint64_t* empty = full + 8;                                                                       // "stage consumed" barriers (one arrival per warp)
     double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES + 128);  // [NV][TMA_NT]
     const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
     const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
         if (part_v && want_v) bulk_g2s_hint(dst + 2 * TMA_TILE, V + i0, bytes, full + st, pol);
     };
     if (tid == 0) {
-        for (int st = 0; st < n_stages; ++st) mbar_init(full + st, 1);
+        for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, TMA_NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, true, false);
     }
@@ -545,8 +549,14 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
             const float4 x0 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2 * TMA_TILE + 2048 + 4 * tid);
             v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
         }
-        __syncthreads();  // every thread holds its part of the stage in registers: the slot can be refilled
-        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages, true, true);
+        // this warp holds its part of the stage in registers; once all 16 warps have said so the slot is refilled.  No
+        // block-wide barrier: warps drift apart by up to the ring depth
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + st);
+        if (tid == 0 && it + n_stages < my_tiles) {
+            while (!mbar_try_wait(empty + st, parity)) {}
+            issue(it + n_stages, true, true);
+        }
 
         const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = i0 + 2048 + 4 * tid;
         if (i0 + TMA_TILE <= a.n) fast2_compute<P, TAU, false, KIND>(a, k, s8, p8, v8, ia, ib, mode, la);
