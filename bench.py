@@ -272,7 +272,9 @@ def main():
                                   "launches_per_step": 1, "ms": prof["gen_kernel_ms"],
                                   "algorithmic_bytes": GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1), "achieved_gbs": gen_gbs,
                                   "frac_hbm": gen_gbs / peak, "traffic": NCU_GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1),
-                                  "instructions_per_path_step": 86, "issue_slot_utilisation": 0.52, "fma_heavy_pipe": 0.57, "xu_pipe": 0.39},
+                                  "instructions_per_path_step": 86, "issue_slot_utilisation": 0.52, "fma_heavy_pipe": 0.57, "xu_pipe": 0.39,
+                                  "fma_pipe_floor_ms_at_2p26": 57.0,
+                                  "frac_of_fma_pipe_floor": (57.0 * n_loc / (1 << 26)) / prof["gen_kernel_ms"]},
         "lsm_sweep_kernel": {"bound": "hbm", "launches_per_step": prof["n_sweep_launches"], "avg_ms": sweep_avg_ms,
                              "total_ms": prof["sweep_kernels_ms"], "algorithmic_bytes_per_launch": lsm_bytes * n_loc,
                              "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak,
@@ -287,8 +289,9 @@ def main():
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dk["achieved_gbs"] / peak, "traffic": dk["traffic"], "peak_source": peak_src,
-                "note": "generator: 86 issued instructions per path-step vs 4 B stored => bound by issue slots and the FMA-heavy pipe (ncu: issue "
-                        "slots 52%, FMA-heavy 57% (Philox IMAD.WIDE + packed fp32x2), XU/SFU 39%, ALU 35%, DRAM 11%; profiles/r01j_summary.md); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
+                "note": "generator: 86 issued instructions per path-step vs 4 B stored => bound by the FMA pipes (Philox's IMAD.WIDE is a 5-clk "
+                        "instruction on B200 and does not overlap fp32 work: 15 x 5 + ~50 clk per warp and path-step = 57 ms floor at 2^26 x 252; "
+                        "ncu: issue slots 52%, FMA-heavy 57%, XU/SFU 39%, ALU 35%, DRAM 11%; profiles/r01j_summary.md, DESIGN 3.1); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
                         "algorithmic 12 B/path, physical traffic 16 B/path (S_{j-1} is read again as the next launch's S_j)",
                 "step_share": {"rbergomi_paths_kernel": prof["gen_kernel_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"]),
                                "lsm_sweep_kernel": prof["sweep_kernels_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"])},
