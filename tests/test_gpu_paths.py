@@ -24,7 +24,7 @@ def _rb(engine, port, n_paths, n, seed, prm=None):
 
 
 @pytest.mark.parametrize("n_paths,n", [(64, 8), (1, 8), (31, 50), (33, 63), (1000, 252), (257, 256), (100, 300), (40, 1000),
-                                       (20, 2047), (7, 1), (5, 2), (9, 3), (4096, 252)])
+                                       (20, 2047), (7, 1), (5, 2), (9, 3), (4096, 252), (33, 252), (1, 200), (50, 130), (999, 129), (64, 255)])
 def test_rbergomi_injected_matches_oracle(engine, port, n_paths, n):
     got, want = _rb(engine, port, n_paths, n, seed=n_paths * 1000 + n)
     assert got.shape == want.shape
