@@ -152,6 +152,12 @@ typedef struct mcp_lsm_result {
 int mcp_lsm_price(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *p, mcp_lsm_result *res,
                   double *coeffs, int32_t *first_exercise, double *v0);
 
+/* n_strikes contracts that differ only in their strike, priced on the SAME path set (prm->strike is ignored).  In
+ * throughput mode (fp32 slab, fp32 carry, one GPU, more than 4096 paths) up to 16 strikes share one sweep: the slab is
+ * read once per step for the whole ladder, one warp per contract.  res: caller's array [n_strikes]. */
+int mcp_lsm_price_multi(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *prm, const double *strikes, int n_strikes,
+                        mcp_lsm_result *res);
+
 /* One call = LSM::PredictOptionPrice(pricePaths, r, strike, maturity, dt, isCall, polyOrder): uploads
  * n_paths host rows of n_cols doubles (kept in fp64 on the device), prices, returns the mean. */
 int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_paths, int n_cols, double r,

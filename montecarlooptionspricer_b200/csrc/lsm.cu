@@ -588,6 +588,186 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// sweep(j) for SEVERAL CONTRACTS ON THE SAME PATHS (strike ladder of a surface, BASELINE config 5): one warp per
+// contract.  The slab tiles S_j | S_{j-1} are fetched once per CTA by the TMA ring and read by all warps from shared
+// memory; the ring also carries every contract's carry tile, each consumed by its own warp.  Per path-step that is 8 B of slab + 8 B of carry per
+// contract instead of 16 B per contract, and the per-launch fixed cost (launch, fold, solve) is paid once for the
+// whole ladder.  Same packed fp32 arithmetic and the same per-contract standardisation as the single-contract
+// throughput kernels.  The last CTA folds the per-CTA moment rows of every contract in a fixed order; warp c solves contract c.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MULTI_MAXC = 16;                 // contracts per launch = warps per CTA
+constexpr int MULTI_TILE = 1024;               // paths per tile
+constexpr int MULTI_STAGE_FLOATS = (2 + MULTI_MAXC) * MULTI_TILE;  // S_j | S_{j-1} | V_0 .. V_15
+constexpr int MULTI_STAGE_BYTES = MULTI_STAGE_FLOATS * 4;
+
+struct MultiArgs {
+    const float* S;
+    int64_t ld, n;
+    float* V;            // [C][ld] carries
+    double* coef;        // [C][M][COEF_LD]
+    const double* mu;    // [C][M]  per-contract standardisation (mean / 1/std of the contract's in-the-money sample)
+    const double* inv_s; // [C][M]
+    double* partial;     // [grid][C][MOM_LD]
+    double* fin;         // [C][4]: sum V0
+    const int* kind;     // [M]
+    unsigned int* counter;
+    double K[MULTI_MAXC];
+    double disc;
+    int C, M, is_call, j, terminal, do_moments, do_final;
+};
+
+template <int P>
+__global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs a, int n_stages) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    constexpr int FLUSH = 8;
+    constexpr int NT = MULTI_MAXC * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES);
+    double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES + 128);  // [NV][NT]
+    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp = contract
+    const bool active = c < a.C;
+    const int cc = active ? c : 0;
+    const float* __restrict__ Sj = a.S + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = a.S + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    float* __restrict__ V = a.V + (int64_t)cc * a.ld;
+    const int mode = a.terminal ? 2 : a.kind[a.j];
+
+    // per-warp constants: this contract's strike, coefficients and standardisation
+    SweepArgs w;  // the view fast2_compute / fast2_load_consts expect
+    memset(&w, 0, sizeof(w));
+    w.n = a.n; w.j = a.j; w.do_moments = a.do_moments; w.do_final = a.do_final; w.is_call = a.is_call; w.disc = a.disc;
+    w.K = a.K[cc];
+    w.d.coef = a.coef + (int64_t)cc * a.M * COEF_LD;
+    w.d.mu = const_cast<double*>(a.mu) + (int64_t)cc * a.M;
+    w.d.inv_s = const_cast<double*>(a.inv_s) + (int64_t)cc * a.M;
+    FastConsts<P> k;
+    fast2_load_consts<P>(w, k);
+    float2 la[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * NT + tid] = 0.0; }
+
+    const int64_t ntile = (a.n + MULTI_TILE - 1) / MULTI_TILE;
+    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint64_t pol = l2_policy_evict_first();
+    auto tile_of = [&](int64_t it) -> int64_t {
+        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
+        return (a.j & 1) ? (ntile - 1 - t) : t;
+    };
+    auto issue = [&](int64_t it) {  // one elected thread: the two slab tiles and every contract's carry tile
+        const int st = (int)(it % n_stages);
+        const int64_t i0 = tile_of(it) * MULTI_TILE;
+        const int64_t cnt = a.ld - i0 < MULTI_TILE ? a.ld - i0 : MULTI_TILE;
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        float* dst = ring + (size_t)st * MULTI_STAGE_FLOATS;
+        mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (mode != 2 ? (uint32_t)a.C : 0u)));
+        bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
+        if (a.do_moments) bulk_g2s(dst + MULTI_TILE, Sp + i0, bytes, full + st);
+        if (mode != 2)
+            for (int q = 0; q < a.C; ++q) bulk_g2s_hint(dst + (2 + q) * MULTI_TILE, a.V + (int64_t)q * a.ld + i0, bytes, full + st, pol);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < n_stages; ++st) mbar_init(full + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it);
+    }
+    __syncthreads();
+
+    int since = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int st = (int)(it % n_stages);
+        const uint32_t parity = (uint32_t)((it / n_stages) & 1);
+        while (!mbar_try_wait(full + st, parity)) {}
+        const float* buf = ring + (size_t)st * MULTI_STAGE_FLOATS;
+        const float* vbuf = buf + (2 + cc) * MULTI_TILE;
+        const int64_t i0 = tile_of(it) * MULTI_TILE;
+        F8 vout[MULTI_TILE / 256];
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < MULTI_TILE / 256; ++g) {  // 256 paths per warp iteration: lane -> 4 + 4 paths
+                const int oa = g * 256 + 4 * lane, ob = oa + 128;
+                const int64_t ia = i0 + oa, ib = i0 + ob;
+                F8 s8, p8;
+                F8& v8 = vout[g];
+                {
+                    const float4 x0 = *reinterpret_cast<const float4*>(buf + oa), x1 = *reinterpret_cast<const float4*>(buf + ob);
+                    s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
+                }
+                p8 = s8; v8 = s8;
+                if (a.do_moments) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + oa), x1 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + ob);
+                    p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
+                }
+                if (mode != 2) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(vbuf + oa), x1 = *reinterpret_cast<const float4*>(vbuf + ob);
+                    v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
+                }
+                if (i0 + MULTI_TILE <= a.n) fast2_compute<P, false, false>(w, k, s8, p8, v8, ia, ib, mode, la);
+                else fast2_compute<P, false, true>(w, k, s8, p8, v8, ia, ib, mode, la);
+                if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
+                if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+                if (++since == FLUSH) {
+#pragma unroll
+                    for (int m = 0; m < NV; ++m) {
+                        sacc[m * NT + tid] += (double)(la[m].x + la[m].y);
+                        la[m] = make_float2(0.f, 0.f);
+                    }
+                    since = 0;
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with the stage: refill it
+        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages);
+    }
+    if (!(a.do_moments || a.do_final)) return;
+    // per-contract (per-warp) partial row of this CTA, in a fixed lane order
+    double acc[NV];
+#pragma unroll
+    for (int m = 0; m < NV; ++m) acc[m] = sacc[m * NT + tid] + (double)(la[m].x + la[m].y);
+    double* prow = a.partial + ((int64_t)blockIdx.x * MULTI_MAXC + c) * MOM_LD;
+#pragma unroll
+    for (int m = 0; m < NV; ++m) {
+        const double sres = warp_sum(acc[m]);
+        if (lane == 0) prow[m] = sres;
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // warp c folds contract c: lane m < NV sums column m over the CTAs in order; lane 0 solves
+    __shared__ double tot[MULTI_MAXC][32];
+    if (active) {
+        double sres = 0.0;
+        if (lane < NV)
+            for (int b = 0; b < (int)gridDim.x; ++b) sres += __ldcg(a.partial + ((int64_t)b * MULTI_MAXC + c) * MOM_LD + lane);
+        tot[c][lane] = sres;
+        __syncwarp();
+        if (lane == 0) {
+            if (a.do_final) a.fin[c * 4] = tot[c][0];
+            else solve_normal_equations<P>(&tot[c][0], a.coef + ((int64_t)c * a.M + (a.j - 1)) * COEF_LD);
+        }
+    }
+    if (tid == 0) *a.counter = 0u;
+}
+
+typedef void (*MultiFn)(MultiArgs, int);
+MultiFn pick_multi(int p) {
+    switch (p) {
+        case 0: return lsm_multi_kernel<0>;
+        case 1: return lsm_multi_kernel<1>;
+        case 2: return lsm_multi_kernel<2>;
+        case 3: return lsm_multi_kernel<3>;
+        case 4: return lsm_multi_kernel<4>;
+        case 5: return lsm_multi_kernel<5>;
+        default: return lsm_multi_kernel<6>;
+    }
+}
+
 // Sum the per-CTA partial rows in a fixed order -> out[0..nv).
 __global__ void __launch_bounds__(256) lsm_reduce_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
     __shared__ double red[8][32];
@@ -1110,6 +1290,117 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
             for (int k = 0; k <= p; ++k) any = any || hcoef[(size_t)j * COEF_LD + k] != 0.0;
             if (!any) { for (int k = 0; k <= p; ++k) out[k] = 0.0; continue; }
             convert_coeffs(&hcoef[(size_t)j * COEF_LD], p, hmu[j], his[j], prm->strike, prm->basis, out);
+        }
+    }
+    return MCP_OK;
+}
+
+// Several strikes on the SAME path set in one sweep (surface ladders, config 5): throughput mode only (fp32 slab,
+// fp32 carry, one GPU).  Other combinations price the strikes one after the other through mcp_lsm_price.
+extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_params* prm, const double* strikes, int n_strikes,
+                                   mcp_lsm_result* res) {
+    if (!ctx || !prm || !strikes || !res || n_strikes <= 0) return MCP_ERR_INVALID;
+    if (!ps || ps->n_paths <= 0) return mcp_fail(ctx, MCP_ERR_EMPTY_PATHS, "LSM::PredictOptionPrice: Empty pricePaths.");
+    if (ps->ctx != ctx) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: pathset belongs to another ctx");
+    const int p = prm->poly_order;
+    if (p < 0) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: poly_order %d < 0", p);
+    if (p > MAXP) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm: poly_order %d > %d", p, MAXP);
+    const int64_t N = ps->n_paths;
+    const bool batched = ps->dtype == MCP_F32 && prm->carry == MCP_F32 && !(ctx->nranks > 1 && ctx->comm) && n_strikes >= 2 && N > SMALL_MAX_PATHS &&
+                         env_int("MCP_LSM_MULTI", 1) != 0;
+    if (!batched) {
+        for (int k = 0; k < n_strikes; ++k) {
+            mcp_lsm_params q = *prm;
+            q.strike = strikes[k];
+            MCP_TRY(mcp_lsm_price(ctx, ps, &q, &res[k], nullptr, nullptr, nullptr));
+        }
+        return MCP_OK;
+    }
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int M = ps->n_steps + 1;
+    const int64_t ld = ps->ld;
+    const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
+    MultiFn fn = pick_multi(p);
+    const size_t fixed = 128 + (size_t)nv * MULTI_MAXC * 32 * 8;
+    int n_stages = (int)((227u * 1024u - 12288u - fixed) / MULTI_STAGE_BYTES);
+    if (n_stages < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm multi: shared memory");
+    const size_t smem = (size_t)n_stages * MULTI_STAGE_BYTES + fixed;
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, MULTI_MAXC * 32, smem, nullptr));
+    const int64_t ntile = (N + MULTI_TILE - 1) / MULTI_TILE;
+    const int grid = (int)(ctx->sm_count < ntile ? ctx->sm_count : ntile);
+    const int grid_aux = (int)((N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4) < (int64_t)ctx->sm_count * 3 ? (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4)
+                                                                                                                   : (int64_t)ctx->sm_count * 3);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_coef = take((size_t)MULTI_MAXC * M * COEF_LD * 8), o_mu = take((size_t)MULTI_MAXC * M * 8), o_is = take((size_t)MULTI_MAXC * M * 8);
+    const size_t o_ssum = take((size_t)M * 4 * 8);
+    const size_t o_part = take((size_t)(grid > grid_aux ? grid : grid_aux) * MULTI_MAXC * MOM_LD * 8), o_fin = take((size_t)MULTI_MAXC * 4 * 8);
+    const size_t o_kind = take((size_t)M * 4), o_cnt = take(4);
+    MCP_TRY(mcp_scratch_reserve(ctx, off));
+    MCP_TRY(mcp_carry_reserve(ctx, (size_t)MULTI_MAXC * ld * 4));
+    unsigned char* sb = (unsigned char*)ctx->scratch;
+    MultiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = (const float*)ps->data; a.ld = ld; a.n = N; a.V = (float*)ctx->carry;
+    a.coef = (double*)(sb + o_coef); a.mu = (double*)(sb + o_mu); a.inv_s = (double*)(sb + o_is);
+    a.partial = (double*)(sb + o_part); a.fin = (double*)(sb + o_fin); a.kind = (int*)(sb + o_kind); a.counter = (unsigned int*)(sb + o_cnt);
+    a.disc = exp(-prm->r * prm->dt); a.M = M; a.is_call = prm->is_call;
+    double* d_ssum = (double*)(sb + o_ssum);
+    std::vector<int> kind(M, STEP_NORMAL);
+    for (int j = 0; j < M; ++j) kind[j] = ((double)j * prm->dt > prm->maturity) ? STEP_DISCOUNT : STEP_NORMAL;
+    cudaStream_t st = ctx->stream;
+    MCP_TRY(mcp_h2d(ctx, (void*)a.kind, kind.data(), (size_t)M * 4));
+    MCP_CUDA(ctx, cudaMemsetAsync(a.counter, 0, 4, st));
+    const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
+    const uint64_t launches0 = ctx->launches;
+    for (int k0 = 0; k0 < n_strikes; k0 += MULTI_MAXC) {
+        const int C = n_strikes - k0 < MULTI_MAXC ? n_strikes - k0 : MULTI_MAXC;
+        a.C = C;
+        for (int c = 0; c < MULTI_MAXC; ++c) a.K[c] = strikes[k0 + (c < C ? c : 0)];
+        MCP_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+        MCP_CUDA(ctx, cudaMemsetAsync(a.coef, 0, (size_t)MULTI_MAXC * M * COEF_LD * 8, st));
+        for (int c = 0; c < MULTI_MAXC; ++c) {  // standardisation of every contract from its own in-the-money sample (as mcp_lsm_price)
+            lsm_scale_sums_kernel<float><<<M, 256, 0, st>>>((const float*)ps->data, ld, ns, a.K[c], prm->is_call, d_ssum);
+            MCP_LAUNCH_CHECK(ctx);
+            lsm_scale_finalize_kernel<<<(M + 127) / 128, 128, 0, st>>>(d_ssum, M, a.K[c], (double*)a.mu + (size_t)c * M, (double*)a.inv_s + (size_t)c * M);
+            MCP_LAUNCH_CHECK(ctx);
+        }
+        for (int j = M - 1; j >= 0; --j) {
+            a.j = j;
+            a.terminal = (j == M - 1);
+            a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
+            a.do_final = (j == 0);
+            fn<<<grid, MULTI_MAXC * 32, smem, st>>>(a, n_stages);
+            MCP_LAUNCH_CHECK(ctx);
+        }
+        // per contract: mean known -> sum of squared deviations (two-pass standard error)
+        const double nloc = (double)N;
+        for (int c = 0; c < C; ++c) {
+            MCP_TRY(mcp_h2d(ctx, a.fin + c * 4 + 2, &nloc, 8));
+            lsm_sqdev_kernel<float><<<grid_aux, LSM_NT, 0, st>>>(a.V + (int64_t)c * ld, N, a.fin + c * 4, a.partial);
+            MCP_LAUNCH_CHECK(ctx);
+            lsm_reduce_kernel<<<1, 256, 0, st>>>(a.partial, grid_aux, 1, a.fin + c * 4 + 1);
+            MCP_LAUNCH_CHECK(ctx);
+        }
+        MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+        double fin[MULTI_MAXC * 4];
+        double* fp = (double*)mcp_stage_alloc(ctx, sizeof(fin));
+        MCP_CUDA(ctx, cudaMemcpyAsync(fp ? fp : fin, a.fin, sizeof(fin), cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, cudaStreamSynchronize(st));
+        MCP_CUDA(ctx, cudaGetLastError());
+        if (fp) memcpy(fin, fp, sizeof(fin));
+        float ms = 0.f;
+        MCP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        for (int c = 0; c < C; ++c) {
+            mcp_lsm_result& r = res[k0 + c];
+            r.sum_v0 = fin[c * 4];
+            r.sum_sq_dev = fin[c * 4 + 1];
+            r.n_paths_global = N;
+            r.price = fin[c * 4] / nloc;
+            const double var = nloc > 1.0 ? fin[c * 4 + 1] / (nloc - 1.0) : 0.0;
+            r.std_error = var > 0.0 ? sqrt(var / nloc) : 0.0;
+            r.elapsed_ms = ms / (float)C;
+            r.n_kernel_launches = (int)(ctx->launches - launches0);
         }
     }
     return MCP_OK;

@@ -41,17 +41,16 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
         cudaEventRecord(e0, ctx->stream);
         rc = mcp_gen_rbergomi(ctx, ps, model, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(mi + 1), path_offset, nullptr, nullptr);
         cudaEventRecord(e1, ctx->stream);
-        for (int k = 0; k < n_strikes && rc == MCP_OK; ++k) {
+        if (rc == MCP_OK) {  // the whole strike ladder of this maturity: one sweep per 16 strikes in throughput mode
             mcp_lsm_params prm = *lsm_tmpl;
-            prm.strike = strikes[k];
             prm.maturity = T;
             prm.dt = model->dt;
-            mcp_lsm_result res;
-            rc = mcp_lsm_price(ctx, ps, &prm, &res, nullptr, nullptr, nullptr);
-            if (rc == MCP_OK) {
-                prices[(size_t)mi * n_strikes + k] = res.price;
-                if (std_errors) std_errors[(size_t)mi * n_strikes + k] = res.std_error;
-                lsm_total += res.elapsed_ms;
+            std::vector<mcp_lsm_result> res((size_t)n_strikes);
+            rc = mcp_lsm_price_multi(ctx, ps, &prm, strikes, n_strikes, res.data());
+            for (int k = 0; k < n_strikes && rc == MCP_OK; ++k) {
+                prices[(size_t)mi * n_strikes + k] = res[(size_t)k].price;
+                if (std_errors) std_errors[(size_t)mi * n_strikes + k] = res[(size_t)k].std_error;
+                lsm_total += res[(size_t)k].elapsed_ms;
             }
         }
         if (rc == MCP_OK) {

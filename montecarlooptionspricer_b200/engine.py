@@ -179,6 +179,14 @@ class Engine:
         return LsmOutput(res.price, res.std_error, res.sum_v0, res.sum_sq_dev, res.n_paths_global, res.elapsed_ms,
                          res.n_kernel_launches, co, fe, v0)
 
+    def lsm_price_multi(self, ps: "PathSet", strikes, r, maturity, dt, is_call, poly_order, carry: int = capi.MCP_F32):
+        """Several strikes on the same path set (one sweep for the whole ladder in throughput mode)."""
+        ks = np.ascontiguousarray(strikes, dtype=np.float64)
+        prm = LsmParams(r, 0.0, maturity, dt, int(bool(is_call)), poly_order, capi.MCP_BASIS_MONOMIAL, carry)
+        res = (LsmResult * max(ks.size, 1))()
+        self._chk(self._L.mcp_lsm_price_multi(self._h, ps._h, C.byref(prm), ks.ctypes.data_as(capi._dp), ks.size, res))
+        return [LsmOutput(x.price, x.std_error, x.sum_v0, x.sum_sq_dev, x.n_paths_global, x.elapsed_ms, x.n_kernel_launches) for x in res[:ks.size]]
+
     def lsm_price_host_rows(self, paths: np.ndarray, r, strike, maturity, dt, is_call, poly_order) -> float:
         """The exact reference call shape: host [N][M] doubles in, the mean out (kept fp64 on the device)."""
         paths = np.ascontiguousarray(paths, dtype=np.float64)

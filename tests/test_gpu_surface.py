@@ -62,3 +62,26 @@ def test_surface_config5_full_size(engine):
     assert np.all(np.diff(atm) > -3 * np.hypot(se[1:, 8], se[:-1, 8]))
     assert np.all(px[:, -1] >= 30.0 - 1e-6)
     print(f"config 5 on one B200: generation {gen_ms:.0f} ms + LSM {lsm_ms:.0f} ms for 256 contracts x 2^22 paths")
+
+
+def test_strike_ladder_in_one_sweep_matches_one_strike_at_a_time(engine, port, monkeypatch):
+    """mcp_lsm_price_multi: up to 16 strikes share one sweep (one warp per contract, slab tiles read once).  Ragged path
+    count, 19 strikes (two launches groups), against the single-contract throughput kernel and the fp64 oracle."""
+    n_paths, n = 300_000 + 77, 16
+    ps = engine.pathset(n_paths, n)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.25, 1.0 / n, seed=8)
+    strikes = np.linspace(82.0, 118.0, 19)
+    multi = engine.lsm_price_multi(ps, strikes, 0.05, 1.0, 1.0 / n, False, 3)
+    assert multi[0].n_kernel_launches < 200  # 2 groups x 17 sweeps + the per-contract standard-error passes
+    monkeypatch.setenv("MCP_LSM_MULTI", "0")
+    single = engine.lsm_price_multi(ps, strikes, 0.05, 1.0, 1.0 / n, False, 3)
+    slab = ps.download_timemajor()
+    ps.close()
+    for k, K in enumerate(strikes):
+        assert multi[k].price == pytest.approx(single[k].price, rel=1e-5)          # same estimator, different standardisation
+        assert multi[k].std_error == pytest.approx(single[k].std_error, rel=1e-4, abs=1e-7)  # K > S0: V0 is one constant
+        assert multi[k].n_paths_global == n_paths
+    for k in (0, 9, 18):
+        want = port.lsm_timemajor_f32(slab, 0.05, float(strikes[k]), 1.0, 1.0 / n, False, 3)
+        assert multi[k].price == pytest.approx(want["price"], rel=1e-5)            # the stated fp32 tolerance
+    assert np.all(np.diff([x.price for x in multi]) > 0)
