@@ -16,9 +16,16 @@
 //   sweep(j):  read S_j, S_{j-1}, V;  apply the step-j decision with the already solved c_j;  write V;  and in
 //              the same pass accumulate the normal-equation moments of step j-1 from the V_j just produced
 //              (fused continuation/exercise update + discounted carry + next regression's X^T X, X^T y).
-//   solve(j-1): one CTA sums the per-CTA fp64 partials in a fixed order (bitwise reproducible), all-reduces
-//              them across GPUs when a communicator is attached (the ONLY data-path collective: 3p+2 doubles),
-//              and solves the (p+1)x(p+1) system.
+//   solve(j-1): the LAST CTA of the same launch to finish (atomic ticket) folds the per-CTA fp64 partials in a
+//              fixed order (bitwise reproducible), all-reduces them across GPUs when a communicator is attached
+//              (the ONLY data-path collective: 3p+2 doubles, exchanged in-kernel through NVLink peer mailboxes
+//              or, as the fallback, by ncclAllReduce between two launches), and solves the (p+1)x(p+1) system.
+//              So a time step is exactly one launch; programmatic dependent launch overlaps step j-1's
+//              prologue with step j's tail.
+// Kernels in this file: the fp64-decision parity kernel (lsm_sweep_kernel), the throughput kernels
+// (lsm_sweep_fast2_kernel: direct 256-bit loads; lsm_sweep_tma_kernel: persistent CTAs fed by a TMA bulk-copy
+// ring), the single-CTA small-problem kernel (lsm_small_kernel) and the multi-contract kernel (lsm_multi_kernel:
+// one pass over the slab prices up to 16 strikes).
 // Regression numerics.  X^T X in raw monomials of S~100 is singular in fp64 (cond ~ 4e17 at config 1), so
 // moments are accumulated in the standardised variable x = (S - mu_j) / s_j (mu_j, s_j = mean / std of the
 // in-the-money prices of a fixed leading sample of paths).  Any basis of the same polynomial space yields the
