@@ -251,7 +251,7 @@ def main():
     e2e_s = float(t.item())
     e2e_value = n_total * N_STEPS * args.steps / e2e_s
     Mp = 256
-    h2d = Mp * (8 + 8 + 4 + 4) + (N_STEPS + 1) * 4 + 8     # phi/twiddle/compensator/position tables, step kinds, N
+    h2d = Mp * (8 + 8 + 4 + 4 + 4) + (N_STEPS + 1) * 4 + 8  # phi/twiddle/compensator/position/spectrum tables, step kinds, N
     d2h = 3 * 8                                            # sum V0, sum sq dev, N
 
     # ---- per-kernel durations (CUDA events around each launch of the two hot kernels; separate, untimed pass) ----
@@ -266,15 +266,15 @@ def main():
     # physical DRAM bytes per launch from the committed `ncu --set full` captures (profiles/r01g_summary.md, 2^26 paths):
     # they scale with the path count, so they are reported per path-step and multiplied out here
     NCU_SWEEP_BYTES_PER_PATH = (805.39e6 + 219.95e6) / (1 << 26)            # S_j + S_{j-1} + V read, V written back
-    NCU_GEN_BYTES_PER_PATHSTEP = (67.86e9 + 0.02e9) / ((1 << 26) * 253.0)   # the slab, written once (profiles/r01j_summary.md)
+    NCU_GEN_BYTES_PER_PATHSTEP = (67.86e9 + 0.01e9) / ((1 << 26) * 253.0)   # the slab, written once (profiles/r01k_summary.md)
     kernels = {
         "rbergomi_paths_kernel": {"bound": "issue slots (FP32/INT + SFU); reported vs its HBM store because the contract asks for it",
                                   "launches_per_step": 1, "ms": prof["gen_kernel_ms"],
                                   "algorithmic_bytes": GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1), "achieved_gbs": gen_gbs,
                                   "frac_hbm": gen_gbs / peak, "traffic": NCU_GEN_BYTES_PER_PATHSTEP * n_loc * (N_STEPS + 1),
-                                  "instructions_per_path_step": 86, "issue_slot_utilisation": 0.52, "fma_heavy_pipe": 0.57, "xu_pipe": 0.39,
-                                  "fma_pipe_floor_ms_at_2p26": 57.0,
-                                  "frac_of_fma_pipe_floor": (57.0 * n_loc / (1 << 26)) / prof["gen_kernel_ms"]},
+                                  "instructions_per_path_step": 58.5, "issue_slot_utilisation": 0.54, "fma_heavy_pipe": 0.56, "xu_pipe": 0.44,
+                                  "fma_pipe_floor_ms_at_2p26": 40.0,
+                                  "frac_of_fma_pipe_floor": (40.0 * n_loc / (1 << 26)) / prof["gen_kernel_ms"]},
         "lsm_sweep_kernel": {"bound": "hbm", "launches_per_step": prof["n_sweep_launches"], "avg_ms": sweep_avg_ms,
                              "total_ms": prof["sweep_kernels_ms"], "algorithmic_bytes_per_launch": lsm_bytes * n_loc,
                              "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak,
@@ -289,9 +289,10 @@ def main():
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dk["achieved_gbs"] / peak, "traffic": dk["traffic"], "peak_source": peak_src,
-                "note": "generator: 86 issued instructions per path-step vs 4 B stored => bound by the FMA pipes (Philox's IMAD.WIDE is a 5-clk "
-                        "instruction on B200 and does not overlap fp32 work: 15 x 5 + ~50 clk per warp and path-step = 57 ms floor at 2^26 x 252; "
-                        "ncu: issue slots 52%, FMA-heavy 57%, XU/SFU 39%, ALU 35%, DRAM 11%; profiles/r01j_summary.md, DESIGN 3.1); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
+                "note": "generator (one complex 256-point transform per PAIR of paths, 2.03 normals per path-step): 58.5 issued instructions per "
+                        "path-step vs 4 B stored => bound by the FMA pipes (Philox's IMAD.WIDE is a 5-clk instruction on B200 and does not overlap "
+                        "fp32 work: 10.2 x 5 + ~38 clk per warp and path-step = 40 ms floor at 2^26 x 252; ncu: issue slots 54%, FMA-heavy 56%, "
+                        "XU/SFU 44%, ALU 35%, DRAM 17%; profiles/r01k_summary.md, DESIGN 3.1); the HBM-bound kernel is lsm_sweep_kernel: frac_hbm below on the "
                         "algorithmic 12 B/path, physical traffic 16 B/path (S_{j-1} is read again as the next launch's S_j)",
                 "step_share": {"rbergomi_paths_kernel": prof["gen_kernel_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"]),
                                "lsm_sweep_kernel": prof["sweep_kernels_ms"] / (prof["gen_kernel_ms"] + prof["lsm_total_ms"])},

@@ -117,8 +117,12 @@ typedef struct mcp_gbm_params {
 /* Fills ps (n_steps, n_paths from the pathset).  Normals: native Philox4x32-10 streams keyed by `seed`
  * and the GLOBAL path id (path_offset + i), or, when `injected` != NULL, host floats in the reference's
  * consumption order: rbergomi [n_paths][4n] = Zre0,Zim0,..,Zre(n-1),Zim(n-1),W1[0..n),W2[0..n)
- * (RoughVolatility.cpp:346-352); gbm [n_paths][n].  `dump` (nullable, same layout) receives the normals
- * actually used, so a native-Philox run can be replayed through the CPU oracle. */
+ * (RoughVolatility.cpp:346-352); gbm [n_paths][n].  `dump` (nullable, same layout) receives draws that
+ * reproduce the generated paths through the reference's own formulas, so a native-Philox run can be replayed
+ * through the CPU oracle: the normals actually used, except for rbergomi with 128 < n_steps <= 256, whose native
+ * stream drives TWO paths with one complex transform (same law, 2 normals per path-step instead of 3;
+ * csrc/gen_rbergomi_pair.cuh) -- there the Z slots hold the per-path draws equivalent to that shared transform.
+ * Either way path i depends on (seed, path_offset + i) only: shards are slices of the whole. */
 int mcp_gen_rbergomi(mcp_ctx *ctx, mcp_pathset *ps, const mcp_rbergomi_params *p, uint64_t seed,
                      uint64_t path_offset, const float *injected, float *dump);
 int mcp_gen_gbm(mcp_ctx *ctx, mcp_pathset *ps, const mcp_gbm_params *p, uint64_t seed, uint64_t path_offset,

@@ -16,8 +16,10 @@
 //   * the M'-point complex DFT runs in shared memory as radix-16 (+ one radix-8/4/2) decimation-in-frequency
 //     passes; output is left digit-reversed and read back through a position table, so there is no
 //     reordering pass.  sqrt(2H) eta / M' and log2(e) are folded into the phi table on the host;
-//   * the benchmark shape (128 < n <= 256 steps) has its own kernel with two paths per thread and packed fp32x2
-//     arithmetic over the pair (gen_rbergomi_x2.cuh); this file's kernel is the generic one (any n <= 4096);
+//   * the benchmark shape (128 < n <= 256 steps) has its own kernels with packed fp32x2 arithmetic: injected draws ->
+//     two paths per thread, one transform per path (gen_rbergomi_x2.cuh); native Philox -> one transform per PAIR of
+//     paths (gen_rbergomi_pair.cuh: same law, a third fewer normals, half the transforms); this file's kernel is the
+//     generic one (any n <= 4096);
 //   * the price recursion is a log-space prefix sum: per-thread serial chunk + one cross-chunk offset, then
 //     S = S0 exp2(.).  fp32 throughout: measured |rel err| vs the fp64 oracle ~3e-7 (tolerance 1e-5).
 #include <math.h>
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(NT, 2) rbergomi_rows_kernel(const RbRow* __res
 }
 
 #include "gen_rbergomi_x2.cuh"
+#include "gen_rbergomi_pair.cuh"
 
 size_t smem_bytes(int Mp, int TP) {
     const int G = NT / TP;
@@ -534,7 +537,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
 
     // device tables (+ slot-major draw tables when injecting / dumping) live in the ctx scratch
     const int Mp = P.Mp;
-    const size_t tab_bytes = (size_t)Mp * (8 + 8 + 4 + 4);
+    const size_t tab_bytes = (size_t)Mp * (8 + 8 + 4 + 4 + 4);
     const bool use_draws = injected || dump;
     const int64_t pc_max = use_draws ? (int64_t)((256u << 20) / ((size_t)4 * n * 4 * 2)) / 32 * 32 : 0;  // paths per draw chunk
     if (use_draws && pc_max < 32) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: draw staging too small for n=%d", n);
@@ -546,6 +549,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
     float2* d_tw = d_phis + Mp;
     float* d_comp2 = (float*)(d_tw + Mp);
     int* d_pos = (int*)(d_comp2 + Mp);
+    float* d_sw = (float*)(d_pos + Mp);  // symmetrised spectrum of the pair stream (gen_rbergomi_pair.cuh)
     float* d_slot = (float*)(base + mcp_round_up((int64_t)tab_bytes, 256));  // [4n][pc]  slot-major
     float* d_rows = d_slot + (size_t)4 * n * pc;                             // [pc][4n]  host order
     {   // the four tables are contiguous on the device: one copy through the pinned ring
@@ -554,6 +558,13 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         memcpy(pack.data() + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
         memcpy(pack.data() + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
         memcpy(pack.data() + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
+        float* sw = (float*)(pack.data() + (size_t)Mp * 24);  // sqrt(w_m), w_m = (|phi_m|^2 + |phi_{M'-m}|^2) / 2, phi_m = 0 for m >= n
+        for (int m = 0; m < Mp; ++m) {
+            const int mm = (Mp - m) & (Mp - 1);
+            const double a = (double)phis[2 * m] * phis[2 * m] + (double)phis[2 * m + 1] * phis[2 * m + 1];
+            const double b = (double)phis[2 * mm] * phis[2 * mm] + (double)phis[2 * mm + 1] * phis[2 * mm + 1];
+            sw[m] = (float)sqrt(0.5 * (a + b));
+        }
         MCP_TRY(mcp_h2d(ctx, d_phis, pack.data(), tab_bytes));
     }
 
@@ -571,13 +582,28 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         }
     };
 
-    // 256-point transforms (128 < n <= 256 steps) run the specialised two-paths-per-thread kernel (gen_rbergomi_x2.cuh);
-    // MCP_GEN_IMPL=0 forces the generic kernel (used by tests that need bit-identical paths from both).
+    // 256-point transforms (128 < n <= 256 steps) run the specialised kernels: injected draws -> two paths per thread, one
+    // transform per path (gen_rbergomi_x2.cuh); native Philox -> one transform per PAIR of paths (gen_rbergomi_pair.cuh; its
+    // own stream, same law).  MCP_GEN_IMPL=2 keeps the per-path stream on the x2 kernel, MCP_GEN_IMPL=0 forces the generic
+    // kernel (per-path stream; used by tests that need bit-identical paths from the batched row driver).
     const char* impl_env = getenv("MCP_GEN_IMPL");
-    const int impl = getenv("MCP_GEN_GENERIC") ? 0 : (impl_env && *impl_env ? atoi(impl_env) : 2);
-    if (Mp == 256 && TP == 32 && impl == 2) {
-        run = [&](const RbParams& Q, const float* din, float* dout, float* out) -> int {
+    const int impl = getenv("MCP_GEN_GENERIC") ? 0 : (impl_env && *impl_env ? atoi(impl_env) : 3);
+    if (Mp == 256 && TP == 32 && impl >= 2) {
+        run = [&, impl](const RbParams& Q, const float* din, float* dout, float* out) -> int {
             const bool inject = din != nullptr, dmp = dout != nullptr;
+            if (!inject && impl >= 3) {
+                void (*kern)(RbParams, PhiloxKeys, const float2*, const float*, const float2*, const float*, float*, float*) =
+                    dmp ? rbergomi_paths_n256pair_kernel<true> : rbergomi_paths_n256pair_kernel<false>;
+                int occ = 0;
+                MCP_TRY(mcp_kernel_config(ctx, (const void*)kern, NT2, PAIR_SMEM, &occ));
+                if (occ < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rbergomi: n256pair kernel does not fit");
+                const int64_t n_tiles = (int64_t)(((Q.path_offset + (uint64_t)Q.n_paths + 63) >> 6) - (Q.path_offset >> 6));
+                int64_t grid = (int64_t)ctx->sm_count * occ;
+                if (grid > n_tiles) grid = n_tiles;
+                kern<<<(unsigned)grid, NT2, PAIR_SMEM, ctx->stream>>>(Q, K, d_phis, d_sw, d_tw, d_comp2, dout, out);
+                MCP_LAUNCH_CHECK(ctx);
+                return MCP_OK;
+            }
             void (*kern)(RbParams, PhiloxKeys, const float2*, const float2*, const float*, const float*, float*, float*);
             if (inject) kern = dmp ? rbergomi_paths_n256x2_kernel<true, true> : rbergomi_paths_n256x2_kernel<true, false>;
             else kern = dmp ? rbergomi_paths_n256x2_kernel<false, true> : rbergomi_paths_n256x2_kernel<false, false>;

@@ -8,6 +8,9 @@
 //   rough-vol W: ctr = (g_lo, g_hi, k>>2, 2) -> four real normals W_{4q..4q+3} (the single N(0,1) that the reference
 //                builds as rho W1 + sqrt(1-rho^2) W2; 3 normals per path-step instead of 4, same law)
 //   gbm        : ctr = (g_lo, g_hi, q, 1)    -> normals of steps 4q .. 4q+3
+//   rough-vol, pair stream (native mode of the 256-point generator, gen_rbergomi_pair.cuh; restated in tests/pair_stream.py):
+//                ctr = (f_lo, f_hi, m>>1, 4) -> spectral normals G_m of transform f = 32 (g >> 6) + (g & 31), shared by paths
+//                g and g ^ 32;  ctr = (g_lo, g_hi, 4 (k & 15) + (k >> 6), 6) -> W_k, lane (k >> 4) & 3
 // with g the GLOBAL path id and key = 64-bit seed.
 #pragma once
 #include <cuda_runtime.h>

@@ -72,9 +72,13 @@ def check_normals(used, ref_draws):
     assert np.mean(err > 2e-5) < 1e-5
 
 
-def test_native_philox_dump_replays_through_oracle(engine, port):
-    """Two-way parity: the normals the GPU actually used, fed to the oracle, reproduce the GPU paths."""
-    n_paths, n = 2000, 252
+@pytest.mark.parametrize("n,impl", [(252, "2"), (252, "0"), (100, None), (300, None)])
+def test_native_philox_dump_replays_through_oracle(engine, port, monkeypatch, n, impl):
+    """Two-way parity on the per-path stream (generic kernel; x2 kernel with MCP_GEN_IMPL=2): the normals the GPU actually
+    used, fed to the oracle, reproduce the GPU paths, and they are the documented Philox / Box-Muller stream."""
+    if impl is not None:
+        monkeypatch.setenv("MCP_GEN_IMPL", impl)
+    n_paths = 2000
     ps = engine.pathset(n_paths, n)
     used = engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"],
                                seed=1234, path_offset=7, dump=True)
@@ -93,6 +97,82 @@ def test_native_philox_dump_replays_through_oracle(engine, port):
         assert abs(x.std() - 1) < 5 / np.sqrt(2 * x.size)
     assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5 / np.sqrt(z.size / 2)
     assert abs(np.corrcoef(w[:, :-1].ravel(), w[:, 1:].ravel())[0, 1]) < 5 / np.sqrt(w.size)
+    ps.close()
+
+
+@pytest.mark.parametrize("n,n_paths,offset", [(252, 2000, 7), (252, 4096, 1 << 33), (129, 333, 64), (200, 70, 31), (256, 130, 0)])
+def test_pair_stream_dump_replays_through_oracle(engine, port, n, n_paths, offset):
+    """The default native stream for 128 < n <= 256 drives two paths with one transform (gen_rbergomi_pair.cuh).  Its dump
+    is, per path, a set of draws in the reference's order that reproduces the path through the reference's formula."""
+    ps = engine.pathset(n_paths, n)
+    used = engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"],
+                               seed=4321, path_offset=offset, dump=True)
+    got = ps.download()
+    assert np.all(np.isfinite(got)) and np.all(got[:, 0] == np.float32(CFG2["S0"]))
+    want = port.rbergomi_paths(CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], n,
+                               used.astype(np.float64))
+    assert np.max(np.abs(got - want) / want) < REL_TOL
+    # without the dump the same paths come out (the dump kernel is a separate instantiation)
+    ps2 = engine.pathset(n_paths, n)
+    engine.gen_rbergomi(ps2, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], seed=4321, path_offset=offset)
+    assert np.array_equal(ps2.download(), got)
+    # W slots: iid N(0,1) split as rho W, sqrt(1-rho^2) W
+    w = CFG2["rho"] * used[:, 2 * n:3 * n].astype(np.float64) + np.sqrt(1 - CFG2["rho"] ** 2) * used[:, 3 * n:].astype(np.float64)
+    assert abs(w.mean()) < 5 / np.sqrt(w.size) and abs(w.std() - 1) < 5 / np.sqrt(2 * w.size)
+    assert abs(np.corrcoef(w[:, :-1].ravel(), w[:, 1:].ravel())[0, 1]) < 5 / np.sqrt(w.size)
+    ps.close()
+    ps2.close()
+
+
+def test_pair_stream_matches_its_written_spec(engine, port):
+    """Philox counters / Box-Muller lanes / Re-Im pairing as documented in gen_rbergomi_pair.cuh, restated in numpy
+    (tests/pair_stream.py): paths 60..67 and 95..97 of a shard starting at global id 1000 (tiles 15, 16, 17)."""
+    import pair_stream
+    n, seed, offset, n_paths = 252, 77, 1000, 200
+    ps = engine.pathset(n_paths, n)
+    engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], seed=seed, path_offset=offset)
+    got = ps.download()
+    loc = [0, 1, 23, 24, 55, 56, 87, 88, 120, 199]
+    d = pair_stream.spec_draws(port, seed, [offset + i for i in loc], n, CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"])
+    want = port.rbergomi_paths(CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], n, d)
+    # fp32 Box-Muller on the SFU (~1e-6 per normal) through a 256-term sum: looser than the injected-draw tolerance
+    assert np.max(np.abs(got[loc] - want) / want) < 1e-4
+    ps.close()
+
+
+def test_pair_stream_has_the_law_of_the_per_path_stream(engine, monkeypatch):
+    """Same model through both native streams, 2^18 paths: moments of the terminal price and of the realised variance
+    agree within Monte-Carlo error, and the two paths that share a transform are uncorrelated."""
+    n, N = 252, 1 << 18
+    stats = {}
+    for impl in ("3", "2"):
+        monkeypatch.setenv("MCP_GEN_IMPL", impl)
+        ps = engine.pathset(N, n)
+        engine.gen_rbergomi(ps, CFG2["S0"], CFG2["r"], CFG2["xi"], CFG2["H"], CFG2["eta"], CFG2["rho"], CFG2["dt"], seed=11)
+        S = ps.download_timemajor().astype(np.float64)  # [n+1][N]
+        ps.close()
+        lr = np.diff(np.log(S), axis=0)
+        rv = (lr ** 2).sum(axis=0)
+        half = (lr[:n // 2] ** 2).sum(axis=0)
+        stats[impl] = dict(ST=S[-1], rv=rv, half=half, lr=lr[[0, 10, 100, 251]])
+    a, b = stats["3"], stats["2"]
+
+    def close(x, y, k=5.0):
+        se = np.sqrt(x.var() / x.size + y.var() / y.size)
+        return abs(x.mean() - y.mean()) < k * se
+
+    assert close(a["ST"], b["ST"])
+    assert close(a["rv"], b["rv"]) and close(a["rv"] ** 2, b["rv"] ** 2)
+    assert close(a["half"], b["half"]) and close(a["half"] * (a["rv"] - a["half"]), b["half"] * (b["rv"] - b["half"]))
+    for i in range(4):
+        assert close(a["lr"][i] ** 2, b["lr"][i] ** 2) and close(a["lr"][i] ** 3, b["lr"][i] ** 3)
+    # Re / Im partners: global ids 64 T + c and 64 T + 32 + c
+    rv = a["rv"].reshape(-1, 2, 32)
+    x, y = np.log(rv[:, 0, :].ravel()), np.log(rv[:, 1, :].ravel())
+    assert abs(np.corrcoef(x, y)[0, 1]) < 5 / np.sqrt(x.size)
+    # neighbours in the packed pair (columns 2 pl, 2 pl + 1) as well
+    x, y = np.log(a["rv"][0::2]), np.log(a["rv"][1::2])
+    assert abs(np.corrcoef(x, y)[0, 1]) < 5 / np.sqrt(x.size)
 
 
 def test_gbm_native_dump_matches_stream_spec(engine, port):
@@ -116,6 +196,18 @@ def test_path_offset_shards_are_slices_of_the_whole(engine):
     for off, cnt in [(0, 1024), (1024, 1024), (2048, 2048), (100, 77)]:
         ps = engine.pathset(cnt, n)
         engine.gen_rbergomi(ps, *args, seed=5, path_offset=off)
+        part = ps.download_timemajor()
+        assert np.array_equal(part, whole[:, off:off + cnt])
+        ps.close()
+    full.close()
+    # the pair stream (128 < n <= 256) keys transforms by the global 64-path tile: odd / unaligned shards are slices too
+    n = 252
+    full = engine.pathset(n_paths, n)
+    engine.gen_rbergomi(full, *args, seed=6, path_offset=1 << 40)
+    whole = full.download_timemajor()
+    for off, cnt in [(0, 1024), (1024, 3072), (100, 77), (33, 95), (63, 2), (1, 4095), (4095, 1)]:
+        ps = engine.pathset(cnt, n)
+        engine.gen_rbergomi(ps, *args, seed=6, path_offset=(1 << 40) + off)
         part = ps.download_timemajor()
         assert np.array_equal(part, whole[:, off:off + cnt])
         ps.close()
