@@ -142,7 +142,8 @@ typedef struct mcp_lsm_params {
 
 typedef struct mcp_lsm_result {
     double price;      /* mean_i V[i][0]                              (LSMPricer.cpp:97-101) */
-    double std_error;  /* [new] sample std of V[:,0] / sqrt(N)        */
+    double std_error;  /* [new] sample std of V[:,0] / sqrt(N): the error of the final average GIVEN the fitted regressions;
+                        * independent runs of this value-iteration estimator scatter 2-4x wider */
     double sum_v0, sum_sq_dev; /* sum_i V0_i and sum_i (V0_i - mean)^2 over ALL ranks */
     int64_t n_paths_global;
     float elapsed_ms;  /* device time of the sweep (CUDA events on the ctx stream) */

@@ -230,9 +230,14 @@ def test_lsm_single_launch_kernel_for_small_path_sets(engine, port, monkeypatch,
 
 def test_config3_full_size_properties(engine):
     """BASELINE config 3 at its full single-GPU size (2^26 paths x 252 steps, cubic basis, 67.9 GB slab) through
-    size-independent properties: determinism (same seed, same bits), agreement within 3 standard errors with an
-    independent 2^22-path price of the same estimator, standard error shrinking like 1/sqrt(N), the American put above
-    its European value on the same paths' law, and the global path count."""
+    size-independent properties: determinism (same seed, same bits), agreement with independent 2^22-path prices of the
+    same estimator within their measured seed-to-seed scatter, standard error shrinking like 1/sqrt(N), the American put
+    above its European value on the same paths' law, and the global path count.
+
+    The reported std_error is sqrt(sample variance of V_0 / N): the error of the final average given the fitted
+    regressions.  The value-iteration estimator (LSMPricer.cpp:78-86 carries FITTED continuation values) also inherits
+    the noise of its 252 regressions, so independent runs scatter 2-4x wider than that (tools/stream_dispersion.py);
+    the comparison below therefore uses the scatter of eight independent small runs, not the reported figure."""
     free = engine.device_info()["free_bytes"]
     if free < 90e9:
         pytest.skip("needs ~70 GB of free HBM")
@@ -241,8 +246,13 @@ def test_config3_full_size_properties(engine):
     big, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 26, 252, seed=3)
     again, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 26, 252, seed=3)
     assert big.price == again.price and big.std_error == again.std_error and big.n_paths_global == 1 << 26
-    small, _ = engine.price_rbergomi_lsm(model, lsm, 1 << 22, 252, seed=4)
-    assert abs(big.price - small.price) < 3 * np.hypot(big.std_error, small.std_error), (big.price, small.price)
+    smalls = [engine.price_rbergomi_lsm(model, lsm, 1 << 22, 252, seed=4 + k)[0] for k in range(8)]
+    small = smalls[0]
+    p = np.array([o.price for o in smalls])
+    sd = p.std(ddof=1)
+    assert sd > small.std_error  # the reported figure is a lower bound of the real scatter
+    # mean of 8 runs (sd / sqrt 8) against one run with 16x the paths (sd / 4); 5 sigma on a 7-dof estimate of sd
+    assert abs(big.price - p.mean()) < 5 * sd * np.sqrt(1 / 8 + 1 / 16), (big.price, p.mean(), sd)
     assert big.std_error == pytest.approx(small.std_error / 4.0, rel=0.02)  # 16x the paths
     euro = dict(lsm, maturity=0.0)  # every step past "maturity" is discount-only: the European value of the terminal payoff
     eu, _ = engine.price_rbergomi_lsm(model, euro, 1 << 22, 252, seed=4)
