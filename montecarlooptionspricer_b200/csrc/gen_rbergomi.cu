@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <functional>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -434,6 +435,38 @@ int launch_tp(mcp_ctx* ctx, const RbParams& P, const PhiloxKeys& K, const float2
 
 }  // namespace
 
+// Process-wide constant tables for the host-side table builder (thread-safe lazy initialisation; engines on
+// different host threads share them).
+namespace {
+struct UnitRoots {
+    std::once_flag once;
+    std::vector<double> c, s;  // cos / sin (2 pi q / 2^lg), q < 2^lg
+};
+UnitRoots g_unit_roots[16];
+const UnitRoots& unit_roots(int lg) {
+    UnitRoots& t = g_unit_roots[lg];
+    std::call_once(t.once, [&] {
+        const int M = 1 << lg;
+        t.c.resize((size_t)M);
+        t.s.resize((size_t)M);
+        for (int q = 0; q < M; ++q) {
+            const double ang = 2.0 * M_PI * (double)q / (double)M;
+            t.c[q] = cos(ang);
+            t.s[q] = sin(ang);
+        }
+    });
+    return t;
+}
+const std::vector<double>& log_table() {  // ln i, i <= 4096 (entry 0 unused)
+    static const std::vector<double> t = [] {
+        std::vector<double> v(4097, 0.0);
+        for (int i = 1; i <= 4096; ++i) v[i] = log((double)i);
+        return v;
+    }();
+    return t;
+}
+}  // namespace
+
 // Host-side tables, all in double then rounded once to fp32.
 //   phi = DFT+(zero-pad(0.5 t^{2H}) to M = nextPow2(n+1))           RoughVolatility.cpp:212-236
 //   phis_k = phi_k * sqrt(2H) eta / M' * log2(e)                    (:270 pads to M' = nextPow2(n); :284 scale; :198-200 1/M')
@@ -444,35 +477,69 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, double xi, std::
     const int M = next_pow2(n + 1), Mp = next_pow2(n);
     const double log2e = 1.4426950408889634074;
     const double log2_xi = xi > 0.0 ? log2(xi) : -INFINITY;  // xi = 0: v = 0 exactly, as xi exp(.) gives
-    std::vector<double> lam(n + 1);
-    for (int i = 0; i <= n; ++i) lam[i] = 0.5 * pow((double)i * dt, 2.0 * H);
+    // t_i^{2H} = exp(2H (ln i + ln dt)), i >= 1: one exp per grid point, shared by lambda and the compensator
+    // (the row driver builds these tables for thousands of rows per call: libm pow / cos / sin per element and an
+    // O(n^2) DFT made it host-bound)
+    const std::vector<double>& ln_i = log_table();
+    const double ln_dt = log(dt);
+    std::vector<double> t2h((size_t)n + 1);
+    t2h[0] = pow(0.0, 2.0 * H);  // 1 for H = 0, else 0
+    for (int i = 1; i <= n; ++i) t2h[i] = exp(2.0 * H * (ln_i[i] + ln_dt));
     const double scale = sqrt(2.0 * H) * eta / (double)Mp * log2e;
     phis.assign((size_t)2 * Mp, 0.f);
-    std::vector<double> cs((size_t)M), sn((size_t)M);  // e^{+2 pi i q / M}, q < M: every term of the DFT below is one of these
-    for (int q = 0; q < M; ++q) {
-        const double ang = 2.0 * M_PI * (double)q / (double)M;
-        cs[q] = cos(ang);
-        sn[q] = sin(ang);
-    }
-    for (int k = 0; k < n; ++k) {
-        double re = 0.0, im = 0.0;
-        int idx = 0;  // (k * i) mod M, advanced incrementally (M is a power of two)
-        for (int i = 0; i <= n; ++i) {
-            re += lam[i] * cs[idx];
-            im += lam[i] * sn[idx];
-            idx = (idx + k) & (M - 1);
+    int lgM = 0;
+    while ((1 << lgM) < M) ++lgM;
+    const UnitRoots& rt = unit_roots(lgM);  // e^{+2 pi i q / M}, q < M: every term of the DFT below is one of these
+    if ((int64_t)n * (n + 1) <= (int64_t)6 * M * lgM) {
+        // short rows: the direct sum is cheaper than a transform
+        for (int k = 0; k < n; ++k) {
+            double re = 0.0, im = 0.0;
+            int idx = 0;  // (k * i) mod M, advanced incrementally (M is a power of two)
+            for (int i = 0; i <= n; ++i) {
+                re += 0.5 * t2h[i] * rt.c[idx];
+                im += 0.5 * t2h[i] * rt.s[idx];
+                idx = (idx + k) & (M - 1);
+            }
+            phis[2 * k] = (float)(re * scale);
+            phis[2 * k + 1] = (float)(im * scale);
         }
-        phis[2 * k] = (float)(re * scale);
-        phis[2 * k + 1] = (float)(im * scale);
+    } else {
+        // radix-2 decimation-in-time transform with the e^{+i theta} kernel (the reference's fft(., +1), RoughVolatility.cpp:171-202)
+        std::vector<double> xr((size_t)M, 0.0), xi_((size_t)M, 0.0);
+        for (int i = 0; i <= n; ++i) {
+            int r = 0;
+            for (int b = 0; b < lgM; ++b) r |= ((i >> b) & 1) << (lgM - 1 - b);
+            xr[r] = 0.5 * t2h[i];
+        }
+        for (int len = 2; len <= M; len <<= 1) {
+            const int half = len >> 1, stride = M / len;
+            for (int base = 0; base < M; base += len)
+                for (int j = 0; j < half; ++j) {
+                    const double wr = rt.c[j * stride], wi = rt.s[j * stride];
+                    const double ur = xr[base + j], ui = xi_[base + j];
+                    const double vr = xr[base + j + half] * wr - xi_[base + j + half] * wi;
+                    const double vi = xr[base + j + half] * wi + xi_[base + j + half] * wr;
+                    xr[base + j] = ur + vr;
+                    xi_[base + j] = ui + vi;
+                    xr[base + j + half] = ur - vr;
+                    xi_[base + j + half] = ui - vi;
+                }
+        }
+        for (int k = 0; k < n; ++k) {
+            phis[2 * k] = (float)(xr[k] * scale);
+            phis[2 * k + 1] = (float)(xi_[k] * scale);
+        }
     }
-    tw.assign((size_t)2 * Mp, 0.f);
-    for (int q = 0; q < Mp; ++q) {
-        const double ang = -2.0 * M_PI * (double)q / (double)Mp;
-        tw[2 * q] = (float)cos(ang);
-        tw[2 * q + 1] = (float)sin(ang);
+    int lgMp = 0;
+    while ((1 << lgMp) < Mp) ++lgMp;
+    const UnitRoots& rp = unit_roots(lgMp);
+    tw.resize((size_t)2 * Mp);
+    for (int q = 0; q < Mp; ++q) {  // e^{-2 pi i q / M'}
+        tw[2 * q] = (float)rp.c[q];
+        tw[2 * q + 1] = (float)(-rp.s[q]);
     }
     comp2.assign((size_t)Mp, 0.f);
-    for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * pow((double)k * dt, 2.0 * H) * log2e + log2_xi);
+    for (int k = 0; k < n; ++k) comp2[k] = (float)(-0.5 * eta * eta * t2h[k] * log2e + log2_xi);
     int lg = 0;
     while ((1 << lg) < Mp) ++lg;
     int radix[8], ns = 0, rem = lg, packed = 0;
