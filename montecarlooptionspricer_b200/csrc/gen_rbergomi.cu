@@ -28,6 +28,7 @@
 
 #include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -728,8 +729,9 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
 int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t model_stride_bytes, const int* n_steps, int n_rows, int n_paths,
                       uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld) {
     std::vector<RbRow> rows((size_t)n_rows);
-    std::vector<unsigned char> tables;
     int max_Mp = 1, live_rows = 0;
+    // pass 1 (serial, trivial): validate, place every row's tables in one staging buffer
+    size_t tables_bytes = 0;
     for (int r = 0; r < n_rows; ++r) {
         const mcp_rbergomi_params* prm = (const mcp_rbergomi_params*)((const unsigned char*)models + (size_t)r * model_stride_bytes);
         RbRow& R = rows[(size_t)r];
@@ -739,32 +741,59 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
         if (n > 512) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: n_steps %d > 512", n);
         if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0))
             return mcp_fail(ctx, MCP_ERR_DOMAIN, "rows: row %d needs dt > 0, H >= 0, |rho| <= 1, xi >= 0", r);
-        std::vector<float> phis, tw, comp2;
-        std::vector<int> pos;
-        mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &R.P.Mp, &R.P.lgMp, &R.P.lg_radix, &R.P.n_stage);
-        const int Mp = R.P.Mp;
-        const double log2e = 1.4426950408889634074;
-        R.P.S0 = (float)prm->S0;
-        R.P.rd2 = (float)(prm->r * prm->dt * log2e);
-        R.P.nkq = (float)(-0.5 / log2e);
-        R.P.lsq = (float)log2(sqrt(prm->dt) * log2e);
-        R.P.rho = (float)prm->rho;
-        R.P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);
-        R.P.n = n;
-        R.P.n_paths = n_paths;
-        R.P.ld = ld;
-        R.P.path_offset = path_offset + (uint64_t)r * (uint64_t)n_paths;
-        R.P.ld_draws = 0;
-        R.table_off = (int64_t)tables.size();
-        R.slab_off = (int64_t)r * slab_stride;
-        const size_t o = tables.size();
-        tables.resize(o + (size_t)Mp * 24);
-        memcpy(tables.data() + o, phis.data(), (size_t)Mp * 8);
-        memcpy(tables.data() + o + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
-        memcpy(tables.data() + o + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
-        memcpy(tables.data() + o + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
+        const int Mp = next_pow2(n);
+        R.P.Mp = Mp;
+        R.table_off = (int64_t)tables_bytes;
+        tables_bytes += (size_t)Mp * 24;
         if (Mp > max_Mp) max_Mp = Mp;
         ++live_rows;
+    }
+    std::vector<unsigned char> tables(tables_bytes);
+    // pass 2: the tables themselves (a few microseconds per row), split over a handful of host threads for large batches
+    auto fill = [&](int r_begin, int r_end) {
+        std::vector<float> phis, tw, comp2;
+        std::vector<int> pos;
+        for (int r = r_begin; r < r_end; ++r) {
+            const int n = n_steps[r];
+            if (n < 1) continue;
+            const mcp_rbergomi_params* prm = (const mcp_rbergomi_params*)((const unsigned char*)models + (size_t)r * model_stride_bytes);
+            RbRow& R = rows[(size_t)r];
+            mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &R.P.Mp, &R.P.lgMp, &R.P.lg_radix, &R.P.n_stage);
+            const int Mp = R.P.Mp;
+            const double log2e = 1.4426950408889634074;
+            R.P.S0 = (float)prm->S0;
+            R.P.rd2 = (float)(prm->r * prm->dt * log2e);
+            R.P.nkq = (float)(-0.5 / log2e);
+            R.P.lsq = (float)log2(sqrt(prm->dt) * log2e);
+            R.P.rho = (float)prm->rho;
+            R.P.rho_c = (float)sqrt(1.0 - prm->rho * prm->rho);
+            R.P.n = n;
+            R.P.n_paths = n_paths;
+            R.P.ld = ld;
+            R.P.path_offset = path_offset + (uint64_t)r * (uint64_t)n_paths;
+            R.P.ld_draws = 0;
+            R.slab_off = (int64_t)r * slab_stride;
+            unsigned char* o = tables.data() + R.table_off;
+            memcpy(o, phis.data(), (size_t)Mp * 8);
+            memcpy(o + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
+            memcpy(o + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
+            memcpy(o + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
+        }
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n_thr = (int)(hw ? hw : 1);
+        if (n_thr > 8) n_thr = 8;
+        if (n_thr > n_rows / 512) n_thr = n_rows / 512;  // small batches: not worth a thread
+        if (n_thr <= 1) {
+            fill(0, n_rows);
+        } else {
+            std::vector<std::thread> pool;
+            const int per = (n_rows + n_thr - 1) / n_thr;
+            for (int t = 1; t < n_thr; ++t) pool.emplace_back(fill, t * per, (t + 1) * per < n_rows ? (t + 1) * per : n_rows);
+            fill(0, per < n_rows ? per : n_rows);
+            for (auto& th : pool) th.join();
+        }
     }
     if (live_rows == 0) return MCP_OK;
     const size_t rows_bytes = (size_t)n_rows * sizeof(RbRow);
