@@ -29,6 +29,29 @@ class LsmOutput:
     v0: Optional[np.ndarray] = None
 
 
+_MODEL_KEYS = ("S0", "r", "xi", "H", "eta", "rho", "dt")
+ROW_DTYPE = np.dtype([("model", np.float64, (7,)), ("n_steps", np.int32), ("is_call", np.int32), ("r", np.float64),
+                      ("strike", np.float64), ("maturity", np.float64), ("dt", np.float64), ("sigma", np.float64),
+                      ("dividend", np.float64)], align=True)  # byte-for-byte mcp_row (include/mcp_b200.h)
+assert ROW_DTYPE.itemsize == C.sizeof(capi.Row) and C.sizeof(capi.RowResult) == 5 * 8
+
+
+def rows_to_array(rows) -> np.ndarray:
+    """mcp_row[] as a numpy structured array (ROW_DTYPE).  A ROW_DTYPE array passes through untouched -- callers with
+    many rows should build that directly; an iterable of dicts (keys as in Engine.price_rows) is converted column-wise."""
+    if isinstance(rows, np.ndarray) and rows.dtype == ROW_DTYPE:
+        return np.ascontiguousarray(rows)
+    rows = list(rows)
+    arr = np.zeros(len(rows), dtype=ROW_DTYPE)
+    if rows:
+        arr["model"] = [[row["model"][k] for k in _MODEL_KEYS] for row in rows]
+        arr["n_steps"] = [int(row["n_steps"]) for row in rows]
+        arr["is_call"] = [1 if row["is_call"] else 0 for row in rows]
+        for k in ("r", "strike", "maturity", "dt", "sigma", "dividend"):
+            arr[k] = [row[k] for row in rows]
+    return arr
+
+
 class Engine:
     """One engine per host thread / per GPU rank (mcp_ctx)."""
 
@@ -223,20 +246,14 @@ class Engine:
         """Batched row driver (mcp_price_rows).  rows: iterable of dicts with keys model (dict of S0, r, xi, H, eta, rho,
         dt), n_steps, is_call, r, strike, maturity, dt, sigma, dividend.  Returns (array [n_rows][5] = asymptotic,
         branching, lsm, martingale, lsm_std_error; gen_ms; price_ms)."""
-        rows = list(rows)
-        arr = (capi.Row * max(len(rows), 1))()
-        for k, row in enumerate(rows):
-            md = row["model"]
-            arr[k].model = RbergomiParams(md["S0"], md["r"], md["xi"], md["H"], md["eta"], md["rho"], md["dt"])
-            arr[k].n_steps, arr[k].is_call = int(row["n_steps"]), int(bool(row["is_call"]))
-            arr[k].r, arr[k].strike, arr[k].maturity, arr[k].dt = row["r"], row["strike"], row["maturity"], row["dt"]
-            arr[k].sigma, arr[k].dividend = row["sigma"], row["dividend"]
-        res = (capi.RowResult * max(len(rows), 1))()
+        arr = rows_to_array(rows)
+        n = int(arr.shape[0])
+        res = np.zeros((max(n, 1), 5), dtype=np.float64)  # mcp_row_result = five doubles
         g, p = C.c_float(), C.c_float()
-        self._chk(self._L.mcp_price_rows(self._h, arr, len(rows), n_paths, poly_order, num_branches, max_iterations, seed,
-                                         path_offset, res, C.byref(g), C.byref(p)))
-        out = np.array([[x.asymptotic, x.branching, x.lsm, x.martingale, x.lsm_std_error] for x in res[:len(rows)]])
-        return out.reshape(len(rows), 5), g.value, p.value
+        self._chk(self._L.mcp_price_rows(self._h, arr.ctypes.data_as(C.POINTER(capi.Row)), n, n_paths, poly_order, num_branches,
+                                         max_iterations, seed, path_offset, res.ctypes.data_as(C.POINTER(capi.RowResult)),
+                                         C.byref(g), C.byref(p)))
+        return res[:n], g.value, p.value
 
     def gbm_nested_dual(self, S0, r, sigma, dt, strike, is_call, n_steps, poly_order, n_policy_paths, n_outer, n_inner,
                         seed: int = 0, path_offset: int = 0) -> dict:

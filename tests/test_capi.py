@@ -94,3 +94,31 @@ def test_cpp_plugins_fail_loudly_without_a_device(tmp_path):
     build.build_all()
     res = subprocess.run([build.DEMO, str(tmp_path / "x.bin"), "1", "8", "30"], capture_output=True, text=True, timeout=120)
     assert res.returncode != 0 and "no CPU fallback" in res.stderr
+
+
+def test_row_marshalling_matches_the_c_struct_byte_for_byte():
+    """Engine.price_rows hands numpy structured arrays to mcp_price_rows: the dtype must be mcp_row exactly."""
+    import ctypes as C
+    import numpy as np
+    from montecarlooptionspricer_b200 import _capi as capi
+    from montecarlooptionspricer_b200.engine import ROW_DTYPE, rows_to_array
+    for name, _ in capi.Row._fields_:
+        assert ROW_DTYPE.fields[name][1] == getattr(capi.Row, name).offset, name
+    rng = np.random.default_rng(3)
+    rows = []
+    for k in range(37):
+        model = dict(S0=rng.uniform(20, 300), r=0.04, xi=rng.uniform(0.01, 0.09), H=rng.uniform(0.05, 0.6), eta=rng.uniform(0.02, 1.9),
+                     rho=rng.uniform(-0.9, 0.0), dt=1 / 252)
+        rows.append(dict(model=model, n_steps=int(rng.integers(0, 300)), is_call=bool(k % 2), r=0.04, strike=rng.uniform(50, 150),
+                         maturity=rng.uniform(0, 1), dt=1 / 252, sigma=0.2, dividend=0.01))
+    want = (capi.Row * len(rows))()
+    for k, row in enumerate(rows):
+        md = row["model"]
+        want[k].model = capi.RbergomiParams(md["S0"], md["r"], md["xi"], md["H"], md["eta"], md["rho"], md["dt"])
+        want[k].n_steps, want[k].is_call = row["n_steps"], int(row["is_call"])
+        want[k].r, want[k].strike, want[k].maturity, want[k].dt = row["r"], row["strike"], row["maturity"], row["dt"]
+        want[k].sigma, want[k].dividend = row["sigma"], row["dividend"]
+    got = rows_to_array(rows)
+    assert got.tobytes() == bytes(want)
+    assert rows_to_array(got) is got or rows_to_array(got).tobytes() == got.tobytes()
+    assert rows_to_array([]).shape == (0,)
