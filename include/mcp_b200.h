@@ -127,6 +127,11 @@ int mcp_gen_rbergomi(mcp_ctx *ctx, mcp_pathset *ps, const mcp_rbergomi_params *p
                      uint64_t path_offset, const float *injected, float *dump);
 int mcp_gen_gbm(mcp_ctx *ctx, mcp_pathset *ps, const mcp_gbm_params *p, uint64_t seed, uint64_t path_offset,
                 const float *injected, float *dump);
+/* Host-side constant tables of the rough-vol generator, for known-answer tests (pure host code, no device):
+ * phis[2 M'] = phi_k sqrt(2H) eta / M' log2(e) for k < n, 0 beyond (RoughVolatility.cpp:212-236, :270, :284, :198-200);
+ * comp2[M'] = -eta^2 t_k^{2H} log2(e) / 2 + log2(xi) (:304); sw[M'] = symmetrised spectrum of the pair stream.
+ * M' = nextPow2(n_steps) is returned (negative = error); outputs are nullable. */
+int mcp_rbergomi_host_tables(int n_steps, const mcp_rbergomi_params *p, float *phis, float *comp2, float *sw);
 /* Raw generator words, for known-answer tests: out[4*i..4*i+3] = Philox4x32-10(ctr=(i_lo,i_hi,c2,c3), key=seed) */
 int mcp_philox_raw(mcp_ctx *ctx, uint64_t seed, uint64_t first, int64_t count, uint32_t c2, uint32_t c3,
                    uint32_t *out_host);

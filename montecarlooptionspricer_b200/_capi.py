@@ -86,6 +86,7 @@ SIGNATURES = {
     "mcp_pathset_download_timemajor_f32": (C.c_int, [_vp, _fp, C.c_int64]),
     "mcp_gen_rbergomi": (C.c_int, [_vp, _vp, C.POINTER(RbergomiParams), C.c_uint64, C.c_uint64, _fp, _fp]),
     "mcp_gen_gbm": (C.c_int, [_vp, _vp, C.POINTER(GbmParams), C.c_uint64, C.c_uint64, _fp, _fp]),
+    "mcp_rbergomi_host_tables": (C.c_int, [C.c_int, C.POINTER(RbergomiParams), _fp, _fp, _fp]),
     "mcp_philox_raw": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32,
                                  C.POINTER(C.c_uint32)]),
     "mcp_lsm_price": (C.c_int, [_vp, _vp, C.POINTER(LsmParams), C.POINTER(LsmResult), _dp, _ip, _dp]),

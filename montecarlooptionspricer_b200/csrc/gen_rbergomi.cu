@@ -569,6 +569,31 @@ int mcp_rbergomi_tables(int n, double H, double eta, double dt, double xi, std::
     return 0;
 }
 
+// sqrt(w_m), w_m = (|phi_m|^2 + |phi_{M'-m}|^2) / 2 with phi_m = 0 for m >= n: the symmetrised spectrum of the pair
+// stream (gen_rbergomi_pair.cuh)
+static void pair_spectrum(const std::vector<float>& phis, int Mp, float* sw) {
+    for (int m = 0; m < Mp; ++m) {
+        const int mm = (Mp - m) & (Mp - 1);
+        const double a = (double)phis[2 * m] * phis[2 * m] + (double)phis[2 * m + 1] * phis[2 * m + 1];
+        const double b = (double)phis[2 * mm] * phis[2 * mm] + (double)phis[2 * mm + 1] * phis[2 * mm + 1];
+        sw[m] = (float)sqrt(0.5 * (a + b));
+    }
+}
+
+// The generator's host-side constant tables, exported for known-answer tests (pure host code: no device, no ctx).
+extern "C" int mcp_rbergomi_host_tables(int n_steps, const mcp_rbergomi_params* prm, float* phis_out, float* comp2_out, float* sw_out) {
+    if (!prm || n_steps < 1 || n_steps > 4096) return MCP_ERR_INVALID;
+    if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(prm->xi >= 0.0)) return MCP_ERR_DOMAIN;
+    std::vector<float> phis, tw, comp2;
+    std::vector<int> pos;
+    int Mp = 0, lgMp = 0, lg_radix = 0, n_stage = 0;
+    mcp_rbergomi_tables(n_steps, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &Mp, &lgMp, &lg_radix, &n_stage);
+    if (phis_out) memcpy(phis_out, phis.data(), (size_t)Mp * 8);
+    if (comp2_out) memcpy(comp2_out, comp2.data(), (size_t)Mp * 4);
+    if (sw_out) pair_spectrum(phis, Mp, sw_out);
+    return Mp;
+}
+
 extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergomi_params* prm, uint64_t seed, uint64_t path_offset,
                                 const float* injected, float* dump) {
     if (!ctx || !ps || !prm) return MCP_ERR_INVALID;
@@ -626,13 +651,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         memcpy(pack.data() + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
         memcpy(pack.data() + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
         memcpy(pack.data() + (size_t)Mp * 20, pos.data(), (size_t)Mp * 4);
-        float* sw = (float*)(pack.data() + (size_t)Mp * 24);  // sqrt(w_m), w_m = (|phi_m|^2 + |phi_{M'-m}|^2) / 2, phi_m = 0 for m >= n
-        for (int m = 0; m < Mp; ++m) {
-            const int mm = (Mp - m) & (Mp - 1);
-            const double a = (double)phis[2 * m] * phis[2 * m] + (double)phis[2 * m + 1] * phis[2 * m + 1];
-            const double b = (double)phis[2 * mm] * phis[2 * mm] + (double)phis[2 * mm + 1] * phis[2 * mm + 1];
-            sw[m] = (float)sqrt(0.5 * (a + b));
-        }
+        pair_spectrum(phis, Mp, (float*)(pack.data() + (size_t)Mp * 24));
         MCP_TRY(mcp_h2d(ctx, d_phis, pack.data(), tab_bytes));
     }
 
@@ -790,8 +809,18 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
         } else {
             std::vector<std::thread> pool;
             const int per = (n_rows + n_thr - 1) / n_thr;
-            for (int t = 1; t < n_thr; ++t) pool.emplace_back(fill, t * per, (t + 1) * per < n_rows ? (t + 1) * per : n_rows);
-            fill(0, per < n_rows ? per : n_rows);
+            int assigned = per < n_rows ? per : n_rows;  // [0, assigned) is this thread's share
+            const int mine = assigned;
+            try {
+                for (int t = 1; t < n_thr && assigned < n_rows; ++t) {
+                    const int end = assigned + per < n_rows ? assigned + per : n_rows;
+                    pool.emplace_back(fill, assigned, end);
+                    assigned = end;
+                }
+            } catch (...) {  // no thread to be had: the rest is done here (nothing may throw across the C ABI)
+            }
+            fill(0, mine);
+            fill(assigned, n_rows);
             for (auto& th : pool) th.join();
         }
     }

@@ -305,6 +305,23 @@ class Engine:
             raise McpError(rc, L.mcp_last_error(None).decode())
         return {k: getattr(out, k) for k in ("S0", "r", "xi", "H", "eta", "rho", "dt")}
 
+    @staticmethod
+    def rbergomi_host_tables(n_steps: int, model: dict) -> dict:
+        """The generator's host-built constant tables (pure host code; known-answer tests): phis complex [M'],
+        comp2 [M'], sw [M'] with M' = nextPow2(n_steps)."""
+        L = capi.lib()
+        prm = RbergomiParams(model["S0"], model["r"], model["xi"], model["H"], model["eta"], model["rho"], model["dt"])
+        Mp = 1
+        while Mp < n_steps:
+            Mp <<= 1
+        phis, comp2, sw = np.zeros(2 * Mp, np.float32), np.zeros(Mp, np.float32), np.zeros(Mp, np.float32)
+        rc = L.mcp_rbergomi_host_tables(n_steps, C.byref(prm), phis.ctypes.data_as(capi._fp), comp2.ctypes.data_as(capi._fp),
+                                        sw.ctypes.data_as(capi._fp))
+        if rc < 0:
+            raise McpError(rc, "mcp_rbergomi_host_tables: invalid arguments")
+        assert rc == Mp
+        return dict(Mp=Mp, phis=phis[0::2].astype(np.float64) + 1j * phis[1::2].astype(np.float64), comp2=comp2, sw=sw)
+
     def generate_stock_price_paths(self, hist, forward_steps: int, path_num: int, seed: int = 0,
                                    path_offset: int = 0) -> np.ndarray:
         h = np.ascontiguousarray(hist, dtype=np.float64)

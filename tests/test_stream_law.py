@@ -56,3 +56,26 @@ def test_pair_stream_w_counter_map_is_a_bijection():
     for k in range(256):
         seen.add((4 * (k & 15) + (k >> 6), (k >> 4) & 3))
     assert len(seen) == 256 and max(c for c, _ in seen) == 63
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 20, 63, 64, 65, 129, 252, 256, 300, 1000, 4096])
+@pytest.mark.parametrize("H,eta,xi", [(0.1, 1.9, 0.04), (0.5, 0.5, 0.09), (0.0, 1.0, 0.02)])
+def test_product_host_tables_match_the_oracle_phi(port, n, H, eta, xi):
+    """The product's host-side table builder (cached unit roots, one exp per grid point, direct sum for short rows and a
+    radix-2 transform for long ones) is pure host arithmetic: check it here against the oracle's phi (the reference's
+    rbergomiPhi, RoughVolatility.cpp:212-236) and the closed forms of the other tables."""
+    import montecarlooptionspricer_b200 as m
+    dt = 1.0 / 252.0
+    t = m.Engine.rbergomi_host_tables(n, dict(S0=100.0, r=0.05, xi=xi, H=H, eta=eta, rho=-0.9, dt=dt))
+    Mp, log2e = t["Mp"], 1.4426950408889634
+    assert Mp >= n and Mp < 2 * max(n, 1) + 1
+    want = np.zeros(Mp, dtype=complex)
+    want[:n] = port.rbergomi_phi(n, H, dt)[:n] * np.sqrt(2 * H) * eta / Mp * log2e
+    scale = np.abs(want).max() if np.abs(want).max() > 0 else 1.0
+    assert np.abs(t["phis"] - want).max() <= 2e-7 * scale  # fp32 rounding of an fp64 result
+    k = np.arange(n)
+    comp = -0.5 * eta * eta * (k * dt) ** (2 * H) * log2e + np.log2(xi)
+    assert np.allclose(t["comp2"][:n], comp, rtol=3e-7, atol=1e-7) and np.all(t["comp2"][n:] == 0)
+    c2 = np.abs(t["phis"]) ** 2
+    w = 0.5 * (c2 + c2[(-np.arange(Mp)) % Mp])
+    assert np.allclose(t["sw"], np.sqrt(w), rtol=2e-7, atol=1e-12 * scale)
