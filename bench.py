@@ -277,7 +277,7 @@ def main():
                                   "frac_of_fma_pipe_floor": (40.0 * n_loc / (1 << 26)) / prof["gen_kernel_ms"]},
         "lsm_sweep_kernel": {"bound": "hbm", "launches_per_step": prof["n_sweep_launches"], "avg_ms": sweep_avg_ms,
                              "total_ms": prof["sweep_kernels_ms"], "algorithmic_bytes_per_launch": lsm_bytes * n_loc,
-                             "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak,
+                             "achieved_gbs": sweep_gbs, "frac_hbm": sweep_gbs / peak, "frac_hbm_nominal_8000": sweep_gbs / 8000.0,
                              "traffic": NCU_SWEEP_BYTES_PER_PATH * n_loc if args.carry == "f32" else None,
                              "physical_gbs": (NCU_SWEEP_BYTES_PER_PATH * n_loc / (sweep_avg_ms * 1e-3) / 1e9) if args.carry == "f32" else None,
                              "lsm_total_ms_incl_solves_and_collectives": prof["lsm_total_ms"]},
