@@ -70,6 +70,8 @@ int mcp_synchronize(mcp_ctx *ctx);
 int mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *free_bytes,
                     size_t *total_bytes);
 uint64_t mcp_launch_count(const mcp_ctx *ctx);  /* kernels launched by this ctx since creation */
+/* bytes this ctx has copied host->device and device->host so far (counted where each copy is issued) */
+int mcp_copy_counters(const mcp_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* Optional per-kernel timing (CUDA events on the ctx stream around every launch of the two hot kernels).
  * Off by default: the extra event records sit between launches and are not wanted in a throughput run. */
@@ -78,6 +80,7 @@ typedef struct mcp_profile {
     float sweep_kernels_ms; /* last mcp_lsm_price: sum over its sweep launches */
     int n_sweep_launches;
     float lsm_total_ms;     /* last mcp_lsm_price: whole backward induction incl. solves / collectives */
+    int n_sweep_steps;      /* time steps those launches swept (the persistent sweep runs all of them in one launch) */
 } mcp_profile;
 int mcp_set_profiling(mcp_ctx *ctx, int on);
 int mcp_get_profile(const mcp_ctx *ctx, mcp_profile *out);

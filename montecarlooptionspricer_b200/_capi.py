@@ -50,7 +50,7 @@ class DualResult(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("gen_kernel_ms", C.c_float), ("sweep_kernels_ms", C.c_float), ("n_sweep_launches", C.c_int),
-                ("lsm_total_ms", C.c_float)]
+                ("lsm_total_ms", C.c_float), ("n_sweep_steps", C.c_int)]
 
 
 _vp = C.c_void_p
@@ -69,6 +69,7 @@ SIGNATURES = {
     "mcp_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mcp_launch_count": (C.c_uint64, [_vp]),
+    "mcp_copy_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mcp_set_profiling": (C.c_int, [_vp, C.c_int]),
     "mcp_get_profile": (C.c_int, [_vp, C.POINTER(Profile)]),
     "mcp_comm_unique_id": (C.c_int, [_vp]),

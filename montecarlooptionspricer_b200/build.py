@@ -44,16 +44,30 @@ def _newer(target: str, deps: list[str]) -> bool:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit (compiled in parallel, rebuilt only when it or a header changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
-        os.path.join(ROOT, "include", "mcp_b200.h")]
-    if not force and _newer(LIB, deps):
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-ldl"]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "mcp_b200.h")]
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.run(cmd, check=True, env=env, cwd=CSRC)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    extra = os.environ.get("MCP_NVCC_EXTRA", "").split()   # e.g. -DMCP_DEBUG_BOUNDS=1
+
+    def one(src: str) -> str:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or extra or not _newer(obj, [src] + hdrs):
+            cmd = [_nvcc()] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            subprocess.run(cmd, check=True, env=env, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(one, srcs))
+    if force or extra or not _newer(LIB, objs):
+        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB, "-ldl"], check=True, env=env)
     return LIB
 
 

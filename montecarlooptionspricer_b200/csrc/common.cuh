@@ -11,8 +11,9 @@
 
 struct McpNccl;  // dlopen'ed NCCL entry points (ctx.cu)
 
-// Mailbox layout: [parity 0|1][source rank][MCP_XROW 8-byte words]; word 2k / 2k+1 = {low / high 32 bits of value k,
-// 32-bit sequence tag}: payload and tag travel in ONE 8-byte store (atomic over NVLink), so no fence and no separate flag.
+// Mailbox layout (legacy per-launch exchange): [parity 0|1][source rank][MCP_XROW 8-byte words]; word 2k / 2k+1 = {low / high
+// 32 bits of value k, 32-bit sequence tag}: payload and tag travel in ONE 8-byte store (atomic over NVLink), so no fence
+// and no separate flag.
 constexpr int MCP_XROW = 64;
 constexpr int MCP_XMAX_RANKS = 16;
 struct McpXchg {
@@ -20,6 +21,25 @@ struct McpXchg {
     int enabled = 0;
     double* const* peer = nullptr;  // device array [nranks]: mailbox base of every rank (own entry = local mailbox)
     int* err = nullptr;             // device flag: set when a wait timed out
+};
+
+// Persistent-sweep exchange (lsm_persist.cuh).  Same tagged-word format.  Two regions:
+//   * the PEER region, part of the IPC-shared mailbox block behind the legacy rows: [parity][source rank][MCP_PX_BIGW words],
+//     written by the reducer CTA of every rank into every rank (one NVLink hop), read locally;
+//   * the LOCAL region (plain cudaMalloc, zeroed once): worker rows [parity][MCP_PX_MAXW][MCP_PX_ROWW] (worker CTA -> reducer CTA)
+//     and broadcast slots [parity][MCP_PX_BCW] (reducer CTA -> worker CTAs).
+constexpr int MCP_PX_BIGW = 4096;
+constexpr int MCP_PX_MAXW = 192;
+constexpr int MCP_PX_ROWW = 48;
+constexpr int MCP_PX_BCW = 32;
+constexpr size_t MCP_XLEGACY_WORDS = (size_t)2 * MCP_XMAX_RANKS * MCP_XROW;
+constexpr size_t MCP_XBOX_WORDS = MCP_XLEGACY_WORDS + (size_t)2 * MCP_XMAX_RANKS * MCP_PX_BIGW;  // whole IPC-shared block
+constexpr size_t MCP_PX_LOCAL_WORDS = (size_t)2 * MCP_PX_MAXW * MCP_PX_ROWW + (size_t)2 * MCP_PX_BCW;
+struct McpPx {
+    unsigned long long* const* peer = nullptr;  // device array [nranks]: base of every rank's IPC block (own entry = local block)
+    unsigned long long* local = nullptr;        // local region
+    int* err = nullptr;
+    int nranks = 1, rank = 0;
 };
 
 // One engine handle per host thread / per GPU rank.
@@ -43,6 +63,7 @@ struct mcp_ctx {
     void* xchg_peer_ptrs_dev = nullptr;    // device copy of xchg.peer[]
     std::vector<void*> xchg_opened;        // peers' mailboxes opened with cudaIpcOpenMemHandle
     unsigned long long xchg_seq = 0;       // exchange counter (all ranks advance in lock step)
+    void* px_local = nullptr;              // local region of the persistent-sweep exchange (see McpPx)
 
     // grow-only device scratch (regression partials, coefficient tables, transposition staging ...)
     void* scratch = nullptr;
@@ -67,7 +88,9 @@ struct mcp_ctx {
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;  // grow-only pool
-    mcp_profile prof = {0.f, 0.f, 0, 0.f};
+    mcp_profile prof = {0.f, 0.f, 0, 0.f, 0};
+    // host<->device bytes moved by this ctx (every copy the library issues is counted where it is issued)
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
 struct mcp_pathset {
@@ -93,6 +116,8 @@ int mcp_h2d(mcp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, int* occ_out);
 // all-reduce (sum, fp64) of a device buffer on ctx->stream; no-op without a communicator
 int mcp_allreduce_f64(mcp_ctx* ctx, double* dev, int count);
+// exchange plumbing of the persistent sweep: allocates the local region (and, without a communicator, a one-rank mailbox block)
+int mcp_px_get(mcp_ctx* ctx, McpPx* out);
 // event `i` of the profiling pool (created on demand)
 cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i);
 
@@ -118,6 +143,13 @@ cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i);
         int rc__ = (expr);             \
         if (rc__ != MCP_OK) return rc__; \
     } while (0)
+
+// every host<->device copy of the product goes through here (or counts itself): bench.py reports the bytes it COUNTED
+static inline cudaError_t mcp_memcpy_async(mcp_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    if (kind == cudaMemcpyHostToDevice) ctx->h2d_bytes += bytes;
+    else if (kind == cudaMemcpyDeviceToHost) ctx->d2h_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
 
 static inline int64_t mcp_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -37,8 +37,10 @@ struct McpNccl {
     bool ok = false;
 };
 static McpNccl g_nccl;
+static std::mutex g_nccl_mu;  // several per-thread engines may call mcp_comm_init / mcp_comm_unique_id at once
 
 static bool nccl_load(std::string* why) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (g_nccl.ok) return true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
@@ -91,18 +93,23 @@ static void xchg_teardown(mcp_ctx* ctx) {
     ctx->xchg = McpXchg();
 }
 
+// Returns with ctx->xchg.enabled = 1 on EVERY rank or on none: every allocation this rank needs is made before the
+// verdict all-reduce, so a local failure is part of the agreed verdict.
 static void xchg_setup(mcp_ctx* ctx) {
     const char* impl = getenv("MCP_COMM_IMPL");
     if (impl && strcmp(impl, "nccl") == 0) return;
     const int n = ctx->nranks;
     if (n < 2 || n > MCP_XMAX_RANKS || !g_nccl.AllGather) return;
-    const size_t box_bytes = (size_t)2 * n * MCP_XROW * sizeof(unsigned long long);
+    if (ctx->xchg_local) xchg_teardown(ctx);  // a one-rank block from an earlier single-GPU price on this ctx
+    const size_t box_bytes = MCP_XBOX_WORDS * sizeof(unsigned long long);
     XchgCard mine;
     memset(&mine, 0, sizeof(mine));
     mine.pid = (long long)getpid();
     mine.device = ctx->device;
     mine.ok = cudaMalloc(&ctx->xchg_local, box_bytes) == cudaSuccess && cudaMemset(ctx->xchg_local, 0, box_bytes) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.handle, ctx->xchg_local) == cudaSuccess;
+              cudaIpcGetMemHandle(&mine.handle, ctx->xchg_local) == cudaSuccess &&
+              cudaMalloc(&ctx->xchg_peer_ptrs_dev, sizeof(double*) * (size_t)n) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->xchg.err, sizeof(int)) == cudaSuccess && cudaMemset(ctx->xchg.err, 0, sizeof(int)) == cudaSuccess;
     cudaGetLastError();
     // all-gather the cards (device staging; the cards are plain bytes)
     XchgCard* d_cards = nullptr;
@@ -125,6 +132,7 @@ static void xchg_setup(mcp_ctx* ctx) {
         ctx->xchg_opened.push_back(p);
         ptrs[(size_t)r] = (double*)p;
     }
+    ok = ok && cudaMemcpy(ctx->xchg_peer_ptrs_dev, ptrs.data(), sizeof(double*) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess;
     cudaGetLastError();
     // every rank must agree, otherwise some would wait on mailboxes nobody writes: all-reduce the verdict
     double* d_flag = nullptr;
@@ -136,23 +144,46 @@ static void xchg_setup(mcp_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(d_flag);
     } else {
-        verdict = 1.0;
+        verdict = 1.0;  // the peers block in their all-reduce until the communicator is torn down: fail loudly upstream
     }
     if (verdict != 0.0) { xchg_teardown(ctx); cudaGetLastError(); return; }
-    if (cudaMalloc(&ctx->xchg_peer_ptrs_dev, sizeof(double*) * (size_t)n) != cudaSuccess || cudaMalloc((void**)&ctx->xchg.err, sizeof(int)) != cudaSuccess) {
-        // cannot happen after the successful allocations above on a healthy device; stay on NCCL, consistently is not
-        // guaranteed here, so fail the setup loudly instead
-        xchg_teardown(ctx);
-        cudaGetLastError();
-        return;
-    }
-    cudaMemcpy(ctx->xchg_peer_ptrs_dev, ptrs.data(), sizeof(double*) * (size_t)n, cudaMemcpyHostToDevice);
-    cudaMemset(ctx->xchg.err, 0, sizeof(int));
     ctx->xchg.nranks = n;
     ctx->xchg.rank = ctx->rank;
     ctx->xchg.peer = (double* const*)ctx->xchg_peer_ptrs_dev;
     ctx->xchg.enabled = 1;
     ctx->xchg_seq = 0;
+}
+
+// Exchange plumbing of the persistent sweep.  With mailboxes up (multi-GPU) it rides on the IPC block; on one GPU (or on
+// the NCCL fallback, where the persistent sweep is not used across ranks) a one-rank block is allocated on first use.
+int mcp_px_get(mcp_ctx* ctx, McpPx* out) {
+    if (!ctx->px_local) {
+        const size_t bytes = MCP_PX_LOCAL_WORDS * sizeof(unsigned long long);
+        if (cudaMalloc(&ctx->px_local, bytes) != cudaSuccess || cudaMemset(ctx->px_local, 0, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            if (ctx->px_local) cudaFree(ctx->px_local);
+            ctx->px_local = nullptr;
+            return mcp_fail(ctx, MCP_ERR_NOMEM, "persistent sweep: local exchange region allocation failed");
+        }
+    }
+    if (!ctx->xchg_local) {  // single rank: own block, own pointer table
+        const size_t box_bytes = MCP_XBOX_WORDS * sizeof(unsigned long long);
+        bool ok = cudaMalloc(&ctx->xchg_local, box_bytes) == cudaSuccess && cudaMemset(ctx->xchg_local, 0, box_bytes) == cudaSuccess &&
+                  cudaMalloc(&ctx->xchg_peer_ptrs_dev, sizeof(void*)) == cudaSuccess &&
+                  cudaMemcpy(ctx->xchg_peer_ptrs_dev, &ctx->xchg_local, sizeof(void*), cudaMemcpyHostToDevice) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->xchg.err, sizeof(int)) == cudaSuccess && cudaMemset(ctx->xchg.err, 0, sizeof(int)) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            xchg_teardown(ctx);
+            return mcp_fail(ctx, MCP_ERR_NOMEM, "persistent sweep: mailbox allocation failed");
+        }
+    }
+    out->peer = (unsigned long long* const*)ctx->xchg_peer_ptrs_dev;
+    out->local = (unsigned long long*)ctx->px_local;
+    out->err = ctx->xchg.err;
+    out->nranks = ctx->xchg.enabled ? ctx->xchg.nranks : 1;
+    out->rank = ctx->xchg.enabled ? ctx->xchg.rank : 0;
+    return MCP_OK;
 }
 
 extern "C" {
@@ -205,6 +236,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     for (auto& blk : ctx->slab_pool) cudaFree(blk.first);
     ctx->slab_pool.clear();
     xchg_teardown(ctx);
+    if (ctx->px_local) cudaFree(ctx->px_local);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->carry) cudaFree(ctx->carry);
@@ -249,6 +281,13 @@ int mcp_device_info(mcp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, s
 
 uint64_t mcp_launch_count(const mcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mcp_copy_counters(const mcp_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!ctx) return MCP_ERR_INVALID;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    return MCP_OK;
+}
+
 int mcp_set_profiling(mcp_ctx* ctx, int on) {
     if (!ctx) return MCP_ERR_INVALID;
     ctx->profiling = on != 0;
@@ -274,9 +313,11 @@ int mcp_comm_unique_id(void* id128) {
 
 int mcp_comm_init(mcp_ctx* ctx, int rank, int nranks, const void* id128) {
     if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return mcp_fail(ctx, MCP_ERR_INVALID, "mcp_comm_init: bad arguments");
+    if (ctx->comm) return mcp_fail(ctx, MCP_ERR_INVALID, "mcp_comm_init: this ctx already has a communicator (one mcp_comm_init per ctx)");
     std::string why;
     if (!nccl_load(&why)) return mcp_fail(ctx, MCP_ERR_NCCL, "%s", why.c_str());
     MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     mcp_nccl_uid uid;
     memcpy(&uid, id128, 128);
     void* comm = nullptr;
@@ -331,6 +372,7 @@ void* mcp_stage_alloc(mcp_ctx* ctx, size_t bytes) {
 
 int mcp_h2d(mcp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (bytes == 0) return MCP_OK;
+    ctx->h2d_bytes += bytes;
     void* pin = mcp_stage_alloc(ctx, bytes);
     if (pin) {
         memcpy(pin, src_host, bytes);

@@ -250,7 +250,7 @@ extern "C" int mcp_gbm_nested_dual(mcp_ctx* ctx, const mcp_gbm_params* model, do
     cudaEventRecord(ev[3], st);
     double h[5] = {0, 0, 0, 0, 0};
     double* hp = (double*)mcp_stage_alloc(ctx, 40);
-    if (rc == MCP_OK && cudaMemcpyAsync(hp ? hp : h, d_fin, 40, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = mcp_fail(ctx, MCP_ERR_CUDA, "dual: D2H failed");
+    if (rc == MCP_OK && mcp_memcpy_async(ctx, hp ? hp : h, d_fin, 40, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = mcp_fail(ctx, MCP_ERR_CUDA, "dual: D2H failed");
     if (rc == MCP_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess))
         rc = mcp_fail(ctx, MCP_ERR_CUDA, "dual: kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
     mcp_pathset_destroy(po);

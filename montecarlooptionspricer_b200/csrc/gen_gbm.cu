@@ -124,7 +124,7 @@ extern "C" int mcp_gen_gbm(mcp_ctx* ctx, mcp_pathset* ps, const mcp_gbm_params* 
         Q.path_offset = path_offset + (uint64_t)p0;
         Q.ld_draws = pc;
         if (injected) {
-            MCP_CUDA(ctx, cudaMemcpyAsync(d_rows, injected + (size_t)p0 * n, (size_t)np * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCP_CUDA(ctx, mcp_memcpy_async(ctx, d_rows, injected + (size_t)p0 * n, (size_t)np * n * 4, cudaMemcpyHostToDevice, ctx->stream));
             mcp_launch_transpose<float, float>(ctx->stream, d_rows, n, np, n, d_slot, pc);
             MCP_LAUNCH_CHECK(ctx);
         }
@@ -132,7 +132,7 @@ extern "C" int mcp_gen_gbm(mcp_ctx* ctx, mcp_pathset* ps, const mcp_gbm_params* 
         if (dump) {
             mcp_launch_transpose<float, float>(ctx->stream, d_slot, pc, n, np, d_rows, n);
             MCP_LAUNCH_CHECK(ctx);
-            MCP_CUDA(ctx, cudaMemcpyAsync(dump + (size_t)p0 * n, d_rows, (size_t)np * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MCP_CUDA(ctx, mcp_memcpy_async(ctx, dump + (size_t)p0 * n, d_rows, (size_t)np * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -156,7 +156,7 @@ extern "C" int mcp_philox_raw(mcp_ctx* ctx, uint64_t seed, uint64_t first, int64
     MCP_TRY(mcp_scratch_reserve(ctx, (size_t)count * 16));
     philox_raw_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(philox_make_keys(seed), first, count, c2, c3, (uint4*)ctx->scratch);
     MCP_LAUNCH_CHECK(ctx);
-    MCP_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->scratch, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, out_host, ctx->scratch, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MCP_OK;
 }

@@ -726,7 +726,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         Q.path_offset = path_offset + (uint64_t)p0;
         Q.ld_draws = pc;
         if (injected) {
-            MCP_CUDA(ctx, cudaMemcpyAsync(d_rows, injected + (size_t)p0 * slots, (size_t)np * slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCP_CUDA(ctx, mcp_memcpy_async(ctx, d_rows, injected + (size_t)p0 * slots, (size_t)np * slots * 4, cudaMemcpyHostToDevice, ctx->stream));
             mcp_launch_transpose<float, float>(ctx->stream, d_rows, slots, np, slots, d_slot, pc);
             MCP_LAUNCH_CHECK(ctx);
         }
@@ -735,7 +735,7 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
         if (dump) {
             mcp_launch_transpose<float, float>(ctx->stream, d_slot, pc, slots, np, d_rows, slots);
             MCP_LAUNCH_CHECK(ctx);
-            MCP_CUDA(ctx, cudaMemcpyAsync(dump + (size_t)p0 * slots, d_rows, (size_t)np * slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MCP_CUDA(ctx, mcp_memcpy_async(ctx, dump + (size_t)p0 * slots, d_rows, (size_t)np * slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -829,8 +829,8 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
     const size_t need = mcp_round_up((int64_t)rows_bytes, 256) + tables.size();
     MCP_TRY(mcp_scratch_reserve(ctx, need));
     unsigned char* base = (unsigned char*)ctx->scratch;
-    MCP_CUDA(ctx, cudaMemcpyAsync(base, rows.data(), rows_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaMemcpyAsync(base + mcp_round_up((int64_t)rows_bytes, 256), tables.data(), tables.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, base, rows.data(), rows_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, base + mcp_round_up((int64_t)rows_bytes, 256), tables.data(), tables.size(), cudaMemcpyHostToDevice, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     const size_t smem = smem_bytes(max_Mp, 32);
     if (smem > 227 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: transform of %d points does not fit", max_Mp);

@@ -276,12 +276,22 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
                                               int mode_rt, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
     const int mode = KIND == 0 ? 0 : mode_rt;
     const bool do_moments = KIND == 0 ? true : (a.do_moments != 0), do_final = KIND == 0 ? false : (a.do_final != 0);
-    const float2(&s)[4] = s8.q;
-    const float2(&sp)[4] = p8.q;
+    float2 s[4], sp[4];
     float2(&v)[4] = v8.q;
     bool ok[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) ok[e] = !TAIL || ((e < 4 ? idx0 : idx1) + (e & 3) < a.n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        s[q] = s8.q[q];
+        sp[q] = p8.q[q];
+        if (TAIL) {
+            // lanes past the last path hold whatever the padding / a stale ring stage held (possibly NaN or Inf bit
+            // patterns, and NaN * 0 = NaN would poison the step's moments): replace them by zeros BEFORE any arithmetic
+            if (!ok[2 * q]) { s[q].x = 0.f; sp[q].x = 0.f; v[q].x = 0.f; }
+            if (!ok[2 * q + 1]) { s[q].y = 0.f; sp[q].y = 0.f; v[q].y = 0.f; }
+        }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float2 pay = __fadd2_rn(__ffma2_rn(s[q], k.sg, k.nsK), k.nsKlo);  // include/core/common.h:8-14
@@ -895,6 +905,22 @@ __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)
     }
 }
 
+#include "lsm_persist.cuh"  // the whole induction in one cooperative launch (uses the step arithmetic and bulk-copy helpers above)
+
+typedef void (*PersistFn)(px::Args);
+template <bool TAU>
+PersistFn pick_persist(int p) {
+    switch (p) {
+        case 0: return px::lsm_persist_kernel<0, TAU>;
+        case 1: return px::lsm_persist_kernel<1, TAU>;
+        case 2: return px::lsm_persist_kernel<2, TAU>;
+        case 3: return px::lsm_persist_kernel<3, TAU>;
+        case 4: return px::lsm_persist_kernel<4, TAU>;
+        case 5: return px::lsm_persist_kernel<5, TAU>;
+        default: return px::lsm_persist_kernel<6, TAU>;
+    }
+}
+
 // Sample statistics for the standardisation: CTA j sums cnt / S / S^2 over the in-the-money prices of the
 // first `ns` paths of row j.
 template <typename ST>
@@ -1127,6 +1153,36 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         }
     }
 
+    // Persistent sweep (one cooperative launch for the whole induction, lsm_persist.cuh): always across GPUs with peer-memory
+    // mailboxes (every rank must follow the same protocol whatever its shard size), and on one GPU when the working set of a
+    // step stays in L2, where the per-launch tail would dominate.  MCP_SWEEP_IMPL=4 forces it, =3 forbids it.
+    const bool multi_early = ctx->nranks > 1 && ctx->comm;
+    const int impl_env = env_int("MCP_SWEEP_IMPL", 0);
+    PersistFn persist = nullptr;
+    int px_workers = 0, px_stages = 0;
+    size_t px_smem = 0;
+    if (!small && ps->dtype == MCP_F32 && carry == MCP_F32 && impl_env != 3 && (!multi_early || ctx->xchg.enabled)) {
+        const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
+        const size_t fixed = 128 + (size_t)nv * px::NT * 8;
+        px_stages = (int)((227u * 1024u - 4096u - fixed) / px::STAGE_BYTES);
+        const int want = env_int("MCP_SWEEP_STAGES", 0);
+        if (want > 0 && want < px_stages) px_stages = want;
+        if (px_stages > 8) px_stages = 8;
+        int64_t w = ntile / (px_stages + 1);
+        const int64_t wmax = (ctx->sm_count - 1 < MCP_PX_MAXW ? ctx->sm_count - 1 : MCP_PX_MAXW);
+        if (w > wmax) w = wmax;
+        if (w < 1) w = 1;
+        const bool l2_fit = (size_t)N * 12 <= ((size_t)env_int("MCP_L2_RESIDENT_MB", 104) << 20);
+        const bool want_px = (multi_early && ctx->xchg.enabled) || impl_env == 4 || (impl_env == 0 && l2_fit && w >= 16);
+        if (want_px && px_stages >= 2) {
+            persist = first_exercise ? pick_persist<true>(p) : pick_persist<false>(p);
+            px_workers = (int)w;
+            px_smem = (size_t)px_stages * px::STAGE_BYTES + fixed;
+            if (px_smem < (size_t)px::RED_SMEM_BYTES) px_smem = px::RED_SMEM_BYTES;
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)persist, px::NT, px_smem, nullptr));
+        }
+    }
+
     // ---- workspace ----
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -1158,8 +1214,9 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     MCP_CUDA(ctx, cudaMemsetAsync(d.counter, 0, 4, st));
 
     // ---- standardisation tables from a fixed leading sample of this rank's paths (summed over ranks) ----
-    // (the single-launch kernel standardises each step itself, from all of its in-the-money prices)
-    if (!small) {
+    // (the single-launch kernel standardises each step itself, from all of its in-the-money prices; the persistent sweep
+    // computes and exchanges the same sample sums inside its launch)
+    if (!small && !persist) {
         const int ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
         if (ps->dtype == MCP_F32) lsm_scale_sums_kernel<float><<<M, 256, 0, st>>>((const float*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
         else lsm_scale_sums_kernel<double><<<M, 256, 0, st>>>((const double*)ps->data, ps->ld, ns, prm->strike, prm->is_call, d.ssum);
@@ -1193,7 +1250,24 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         MCP_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 1), st);
     }
-    for (int j = M - 1; j >= 0 && !small; --j) {
+    if (persist) {
+        px::Args pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.S = (const float*)ps->data; pa.ld = ps->ld; pa.n = N; pa.V = (float*)dV; pa.tau = dTau;
+        pa.coef = d.coef; pa.mu = d.mu; pa.inv_s = d.inv_s; pa.ssum = d.ssum; pa.fin = d.fin; pa.kind = d.kind;
+        pa.K = prm->strike; pa.disc = disc; pa.is_call = prm->is_call; pa.M = M;
+        pa.ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
+        pa.l2_resident = a.l2_resident; pa.n_workers = px_workers; pa.n_stages = px_stages;
+        MCP_TRY(mcp_px_get(ctx, &pa.x));
+        pa.seq0 = ctx->xchg_seq + 1;
+        ctx->xchg_seq += px::exchanges_per_launch(M, kind.data());
+        void* kargs[] = {(void*)&pa};
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 0), st);
+        MCP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)persist, dim3((unsigned)(px_workers + 1)), dim3(px::NT), kargs, px_smem, st));
+        MCP_LAUNCH_CHECK(ctx);
+        if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 1), st);
+    }
+    for (int j = M - 1; j >= 0 && !small && !persist; --j) {
         a.j = j;
         a.terminal = (j == M - 1);
         a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
@@ -1226,7 +1300,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     }
     // ---- payoff averaging: sum V0 (+ N) -> global mean -> sum of squared deviations ----
     double fin[3] = {0, 0, 0};  // d.fin[0] = sum V0 was written by the last CTA of sweep(0)
-    if (!small) {
+    if (!small && !persist) {
         const double nloc = (double)N;
         if (!p2p) MCP_TRY(mcp_h2d(ctx, d.fin + 2, &nloc, 8));
         if (!p2p) MCP_TRY(mcp_allreduce_f64(ctx, d.fin, 3));  // fin[1] is overwritten below; with mailboxes sweep(0) already left the global {sum V0, N}
@@ -1239,27 +1313,30 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     }  // the single-launch kernel leaves {sum V0, sum (V0 - mean)^2, N} itself
     MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     double* fin_pin = (double*)mcp_stage_alloc(ctx, 3 * 8);
-    MCP_CUDA(ctx, cudaMemcpyAsync(fin_pin ? fin_pin : fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, fin_pin ? fin_pin : fin, d.fin, 3 * 8, cudaMemcpyDeviceToHost, st));
     if (dV0) {
         if (carry == MCP_F32) lsm_copy_v0_kernel<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const float*)dV, N, dV0);
         else lsm_copy_v0_kernel<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const double*)dV, N, dV0);
         MCP_LAUNCH_CHECK(ctx);
-        MCP_CUDA(ctx, cudaMemcpyAsync(v0, dV0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, v0, dV0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (dTau) MCP_CUDA(ctx, cudaMemcpyAsync(first_exercise, dTau, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (dTau) MCP_CUDA(ctx, mcp_memcpy_async(ctx, first_exercise, dTau, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     std::vector<double> hcoef, hmu, his;
     if (coeffs) {
         hcoef.resize((size_t)M * COEF_LD); hmu.resize(M); his.resize(M);
-        MCP_CUDA(ctx, cudaMemcpyAsync(hcoef.data(), d.coef, (size_t)M * COEF_LD * 8, cudaMemcpyDeviceToHost, st));
-        MCP_CUDA(ctx, cudaMemcpyAsync(hmu.data(), d.mu, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-        MCP_CUDA(ctx, cudaMemcpyAsync(his.data(), d.inv_s, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, hcoef.data(), d.coef, (size_t)M * COEF_LD * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, hmu.data(), d.mu, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, his.data(), d.inv_s, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
     }
     int xerr = 0;
-    if (p2p) MCP_CUDA(ctx, cudaMemcpyAsync(&xerr, ctx->xchg.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if ((p2p || persist) && ctx->xchg.err) MCP_CUDA(ctx, mcp_memcpy_async(ctx, &xerr, ctx->xchg.err, sizeof(int), cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     MCP_CUDA(ctx, cudaGetLastError());
     if (fin_pin) memcpy(fin, fin_pin, 3 * 8);
-    if (xerr) return mcp_fail(ctx, MCP_ERR_NCCL, "lsm: peer-memory moment exchange timed out (a rank did not reach the same sweep step)");
+    if (xerr) {
+        cudaMemsetAsync(ctx->xchg.err, 0, sizeof(int), st);  // reported once; the next call starts clean
+        return mcp_fail(ctx, MCP_ERR_NCCL, "lsm: peer-memory moment exchange timed out (a rank did not reach the same sweep step)");
+    }
 
     const double ng = fin[2];
     res->sum_v0 = fin[0];
@@ -1274,8 +1351,9 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     ctx->prof.lsm_total_ms = ms;
     ctx->prof.sweep_kernels_ms = 0.f;
     ctx->prof.n_sweep_launches = 0;
+    ctx->prof.n_sweep_steps = M;
     if (ctx->profiling) {
-        for (int j = 0; j < (small ? 1 : M); ++j) {
+        for (int j = 0; j < ((small || persist) ? 1 : M); ++j) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, mcp_prof_event(ctx, 2 * (size_t)j), mcp_prof_event(ctx, 2 * (size_t)j + 1)) == cudaSuccess)
                 ctx->prof.sweep_kernels_ms += t;
@@ -1392,7 +1470,7 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
         MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
         double fin[MULTI_MAXC * 4];
         double* fp = (double*)mcp_stage_alloc(ctx, sizeof(fin));
-        MCP_CUDA(ctx, cudaMemcpyAsync(fp ? fp : fin, a.fin, sizeof(fin), cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, fp ? fp : fin, a.fin, sizeof(fin), cudaMemcpyDeviceToHost, st));
         MCP_CUDA(ctx, cudaStreamSynchronize(st));
         MCP_CUDA(ctx, cudaGetLastError());
         if (fp) memcpy(fin, fp, sizeof(fin));

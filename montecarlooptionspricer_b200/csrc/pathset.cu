@@ -35,14 +35,24 @@ int mcp_pathset_create(mcp_ctx* ctx, int64_t n_paths, int n_steps, int dtype, mc
         ps->capacity = ctx->slab_pool[best].second;
         ctx->slab_pool_bytes -= ps->capacity;
         ctx->slab_pool.erase(ctx->slab_pool.begin() + best);
-        *out = ps;
-        return MCP_OK;
+    } else {
+        ps->capacity = ps->bytes;
+        if (cudaMalloc(&ps->data, ps->bytes) != cudaSuccess) {
+            cudaGetLastError();
+            delete ps;
+            return mcp_fail(ctx, MCP_ERR_NOMEM, "pathset: cudaMalloc of %zu bytes failed", (size_t)ps->bytes);
+        }
     }
-    ps->capacity = ps->bytes;
-    if (cudaMalloc(&ps->data, ps->bytes) != cudaSuccess) {
-        cudaGetLastError();
-        delete ps;
-        return mcp_fail(ctx, MCP_ERR_NOMEM, "pathset: cudaMalloc of %zu bytes failed", (size_t)ps->bytes);
+    // generators and uploads write live paths only: the pad columns [n_paths, ld) of every row start as zeros, so the
+    // vector / bulk-copy readers that touch them never see recycled NaN or Inf bit patterns
+    if (ps->ld > n_paths) {
+        const size_t esz = dtype == MCP_F32 ? 4 : 8;
+        cudaError_t e = cudaMemset2DAsync((char*)ps->data + (size_t)n_paths * esz, (size_t)ps->ld * esz, 0, (size_t)(ps->ld - n_paths) * esz,
+                                          (size_t)(n_steps + 1), ctx->stream);
+        if (e != cudaSuccess) {
+            mcp_pathset_destroy(ps);
+            return mcp_fail(ctx, MCP_ERR_CUDA, "pathset: clearing the pad columns failed: %s", cudaGetErrorString(e));
+        }
     }
     *out = ps;
     return MCP_OK;
@@ -109,6 +119,7 @@ int mcp_pathset_upload_f64(mcp_pathset* ps, const double* host, int64_t ld_host)
     MCP_TRY(mcp_scratch_reserve(ctx, (size_t)pc * cols * 8));
     for (int64_t p0 = 0; p0 < ps->n_paths; p0 += pc) {
         const int64_t n = (ps->n_paths - p0 < pc) ? ps->n_paths - p0 : pc;
+        ctx->h2d_bytes += (size_t)cols * 8 * (size_t)n;
         MCP_CUDA(ctx, cudaMemcpy2DAsync(ctx->scratch, (size_t)cols * 8, host + p0 * ld_host, (size_t)ld_host * 8,
                                         (size_t)cols * 8, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         MCP_TRY(scatter_chunk(ps, (const double*)ctx->scratch, p0, n));
@@ -129,7 +140,7 @@ int mcp_pathset_upload_rows_f64(mcp_pathset* ps, const double* const* rows) {
         const int64_t n = (ps->n_paths - p0 < pc) ? ps->n_paths - p0 : pc;
         double* pin = (double*)ctx->pinned;
         for (int64_t i = 0; i < n; ++i) memcpy(pin + i * cols, rows[p0 + i], (size_t)cols * 8);
-        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, pin, (size_t)n * cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, ctx->scratch, pin, (size_t)n * cols * 8, cudaMemcpyHostToDevice, ctx->stream));
         MCP_TRY(scatter_chunk(ps, (const double*)ctx->scratch, p0, n));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -152,6 +163,7 @@ int mcp_pathset_download_f64(const mcp_pathset* ps, double* host, int64_t ld_hos
         else
             mcp_launch_transpose<double, double>(ctx->stream, (const double*)ps->data + p0, ps->ld, cols, n, stage, cols);
         MCP_LAUNCH_CHECK(ctx);
+        ctx->d2h_bytes += (size_t)cols * 8 * (size_t)n;
         MCP_CUDA(ctx, cudaMemcpy2DAsync(host + p0 * ld_host, (size_t)ld_host * 8, stage, (size_t)cols * 8, (size_t)cols * 8,
                                         (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -176,7 +188,7 @@ int mcp_pathset_download_rows_f64(const mcp_pathset* ps, double* const* rows) {
             mcp_launch_transpose<double, double>(ctx->stream, (const double*)ps->data + p0, ps->ld, cols, n, stage, cols);
         MCP_LAUNCH_CHECK(ctx);
         double* pin = (double*)ctx->pinned;
-        MCP_CUDA(ctx, cudaMemcpyAsync(pin, stage, (size_t)n * cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, pin, stage, (size_t)n * cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (int64_t i = 0; i < n; ++i) memcpy(rows[p0 + i], pin + i * cols, (size_t)cols * 8);
     }
@@ -189,6 +201,7 @@ int mcp_pathset_download_timemajor_f32(const mcp_pathset* ps, float* host, int64
     if (ps->dtype != MCP_F32) return mcp_fail(ctx, MCP_ERR_INVALID, "download_timemajor_f32: slab is not fp32");
     if (ld_host < ps->n_paths) return mcp_fail(ctx, MCP_ERR_INVALID, "download: ld_host too small");
     MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->d2h_bytes += (size_t)ps->n_paths * 4 * (size_t)(ps->n_steps + 1);
     MCP_CUDA(ctx, cudaMemcpy2DAsync(host, (size_t)ld_host * 4, ps->data, (size_t)ps->ld * 4, (size_t)ps->n_paths * 4,
                                     (size_t)(ps->n_steps + 1), cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -402,7 +402,7 @@ extern "C" int mcp_asymptotic_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     MCP_TRY(mcp_allreduce_f64(ctx, d_out, 2));
     double h[2] = {0, 0};
     double* hp = (double*)mcp_stage_alloc(ctx, 16);
-    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_out, 16, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, hp ? hp : h, d_out, 16, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     if (hp) memcpy(h, hp, 16);
     *price = h[1] > 0.0 ? h[0] / h[1] : 0.0;  // :108
@@ -463,7 +463,7 @@ extern "C" int mcp_martingale_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
         MCP_LAUNCH_CHECK(ctx);
         double h2[8];
         double* hp2 = (double*)mcp_stage_alloc(ctx, 64);
-        MCP_CUDA(ctx, cudaMemcpyAsync(hp2 ? hp2 : h2, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, hp2 ? hp2 : h2, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
         MCP_CUDA(ctx, cudaStreamSynchronize(st));
         if (hp2) memcpy(h2, hp2, 64);
         const double primal = h2[5] / (double)N, dual = h2[6] / (double)N;
@@ -513,7 +513,7 @@ extern "C" int mcp_martingale_price(mcp_ctx* ctx, const mcp_pathset* ps, double 
     }
     double h[8];
     double* hp = (double*)mcp_stage_alloc(ctx, 64);
-    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, hp ? hp : h, d_fin, 8 * 8, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     if (hp) memcpy(h, hp, 64);
     const double primal = h[0] / h[1];
@@ -583,7 +583,7 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
     if (small) {
         // one launch: both bounds
         MCP_TRY(mcp_h2d(ctx, d_isex, is_ex.data(), (size_t)M * 4));
-        if (d_inj) MCP_CUDA(ctx, cudaMemcpyAsync(d_inj, injected_rp, (size_t)n_ex * N * num_branches * 4, cudaMemcpyHostToDevice, st));
+        if (d_inj) MCP_CUDA(ctx, mcp_memcpy_async(ctx, d_inj, injected_rp, (size_t)n_ex * N * num_branches * 4, cudaMemcpyHostToDevice, st));
         const int j_hi = kend - 1 > exercise_times[n_ex - 1] ? kend - 1 : exercise_times[n_ex - 1];
         const size_t smem = (size_t)2 * N * sizeof(double);
         if (f32) {
@@ -609,7 +609,7 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
         for (int j = j_hi; j >= exercise_times[0]; --j) {
             const int e = is_ex[j];
             if (e && d_inj) {
-                MCP_CUDA(ctx, cudaMemcpyAsync(d_inj, injected_rp + (size_t)(e - 1) * N * num_branches, (size_t)N * num_branches * 4, cudaMemcpyHostToDevice, st));
+                MCP_CUDA(ctx, mcp_memcpy_async(ctx, d_inj, injected_rp + (size_t)(e - 1) * N * num_branches, (size_t)N * num_branches * 4, cudaMemcpyHostToDevice, st));
             }
             const int j_valid = j < kend ? 1 : 0;  // index j enters the future maxima of earlier dates only if t_j <= maturity
             const int has_cont = j < ex_back ? 1 : 0;
@@ -629,7 +629,7 @@ extern "C" int mcp_branching_price(mcp_ctx* ctx, const mcp_pathset* ps, double r
     MCP_TRY(mcp_allreduce_f64(ctx, d_fin, 3));
     double h[3];
     double* hp = (double*)mcp_stage_alloc(ctx, 24);
-    MCP_CUDA(ctx, cudaMemcpyAsync(hp ? hp : h, d_fin, 24, cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, hp ? hp : h, d_fin, 24, cudaMemcpyDeviceToHost, st));
     MCP_CUDA(ctx, cudaStreamSynchronize(st));
     if (hp) memcpy(h, hp, 24);
     const double lower = h[0] / h[2], upper = h[1] / h[2];

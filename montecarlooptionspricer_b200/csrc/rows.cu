@@ -139,11 +139,11 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
                                slab_stride, ld);
         if (rc != MCP_OK) break;
         cudaEventRecord(e1, ctx->stream);
-        if (cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: H2D failed"); break; }
+        if (mcp_memcpy_async(ctx, d_rows, h_rows.data(), (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: H2D failed"); break; }
         fn<<<nr, SB_NT, smem, ctx->stream>>>(d_rows, d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_out);
         ctx->launches++;
         cudaEventRecord(e2, ctx->stream);
-        if (cudaMemcpyAsync(h_out.data(), d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        if (mcp_memcpy_async(ctx, h_out.data(), d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
             rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: pricing kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;

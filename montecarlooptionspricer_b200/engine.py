@@ -104,6 +104,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._L.mcp_launch_count(self._h))
 
+    def copy_counters(self) -> tuple:
+        """(host->device bytes, device->host bytes) this engine has copied so far, counted inside the library."""
+        h, d = C.c_uint64(), C.c_uint64()
+        self._chk(self._L.mcp_copy_counters(self._h, C.byref(h), C.byref(d)))
+        return int(h.value), int(d.value)
+
     def set_profiling(self, on: bool):
         self._chk(self._L.mcp_set_profiling(self._h, int(on)))
 
@@ -111,7 +117,7 @@ class Engine:
         p = capi.Profile()
         self._chk(self._L.mcp_get_profile(self._h, C.byref(p)))
         return dict(gen_kernel_ms=p.gen_kernel_ms, sweep_kernels_ms=p.sweep_kernels_ms,
-                    n_sweep_launches=p.n_sweep_launches, lsm_total_ms=p.lsm_total_ms)
+                    n_sweep_launches=p.n_sweep_launches, lsm_total_ms=p.lsm_total_ms, n_sweep_steps=p.n_sweep_steps)
 
     # -- multi-GPU --------------------------------------------------------------------------------
     @staticmethod

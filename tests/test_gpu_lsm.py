@@ -257,3 +257,81 @@ def test_config3_full_size_properties(engine):
     euro = dict(lsm, maturity=0.0)  # every step past "maturity" is discount-only: the European value of the terminal payoff
     eu, _ = engine.price_rbergomi_lsm(model, euro, 1 << 22, 252, seed=4)
     assert small.price > eu.price > 0.0
+
+
+def _poison_padding(ps):
+    """Fill the pad columns [n_paths, ld) of every slab row with 0xFF bytes (a NaN bit pattern in fp32)."""
+    from cuda.bindings import runtime as rt
+    info = ps.info()
+    pad = info["ld"] - info["n_paths"]
+    if pad <= 0:
+        return 0
+    esz = 4 if info["dtype"] == m.MCP_F32 else 8
+    (err,) = rt.cudaMemset2D(info["device_ptr"] + info["n_paths"] * esz, info["ld"] * esz, 0xFF, pad * esz, info["n_steps"] + 1)
+    assert int(err) == 0, err
+    (err,) = rt.cudaDeviceSynchronize()
+    assert int(err) == 0, err
+    return pad
+
+
+@pytest.mark.parametrize("impl", ["2", "3", "4"])
+def test_lsm_throughput_kernels_ignore_nan_in_the_padding(engine, port, monkeypatch, impl):
+    """Pad lanes of a slab row (and stale ring bytes behind a short tail tile) may hold any bit pattern; a NaN there must
+    not reach the regression moments (NaN * 0 = NaN).  The three throughput sweeps price a ragged path set whose padding
+    was filled with NaN on purpose exactly as they price the clean one."""
+    n_paths, n = 2 * 148 * 4096 + 4096 + 77, 8   # 77 live lanes in the last 128-lane line, short tail tile
+    ps = engine.pathset(n_paths, n)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.2, 1.0 / n, seed=15)
+    monkeypatch.setenv("MCP_SWEEP_IMPL", impl)
+    clean = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / n, False, 3, carry=m.MCP_F32)
+    assert _poison_padding(ps) == 128 - 77
+    dirty = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / n, False, 3, carry=m.MCP_F32)
+    assert np.isfinite(dirty.price) and dirty.price == clean.price and dirty.std_error == clean.std_error
+    multi = engine.lsm_price_multi(ps, [95.0, 100.0, 105.0], 0.05, 1.0, 1.0 / n, False, 3)
+    assert all(np.isfinite(o.price) and o.price > 0 for o in multi)
+    ps.close()
+
+
+@pytest.mark.parametrize("n_paths,n,p,is_call,K,T", [
+    (5 * 147 * 4096 + 3 * 4096 + 77, 12, 3, False, 100.0, 1.0),   # every worker busy, uneven tile counts, ragged tail
+    (5 * 147 * 4096 + 3 * 4096 + 77, 12, 3, True, 97.0, 1.0),
+    (40 * 4096 + 1, 30, 2, False, 103.0, 1.0),                    # a few workers, 1-path tail tile
+    (9000, 20, 3, False, 100.0, 1.0),                             # fewer tiles than ring stages: per-step refill mode
+    (300_000, 24, 4, False, 100.0, 0.5),                          # maturity cut: discount-only steps before the first regression
+    (300_000, 10, 0, False, 101.0, 1.0), (300_000, 10, 1, False, 101.0, 1.0), (200_000, 10, 5, False, 101.0, 1.0),
+    (200_000, 10, 6, False, 101.0, 1.0),
+])
+def test_lsm_persistent_sweep_matches_per_step_kernels_and_oracle(engine, port, monkeypatch, n_paths, n, p, is_call, K, T):
+    """The persistent cooperative sweep (whole induction in one launch: worker CTAs on a TMA ring that runs across step
+    boundaries, a reducer CTA that folds / solves / broadcasts) against the per-step kernels on the same slab and, for
+    p <= 4, against the fp64 oracle within the stated 1e-5."""
+    ps = engine.pathset(n_paths, n)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.2, 1.0 / n, seed=n_paths % 1000 + p)
+    monkeypatch.setenv("MCP_LSM_SMALL", "0")
+    monkeypatch.setenv("MCP_SWEEP_IMPL", "4")
+    got = engine.lsm_price(ps, 0.05, K, T, 1.0 / n, is_call, p, carry=m.MCP_F32, want_first_exercise=True, want_v0=True, want_coeffs=True)
+    assert got.n_kernel_launches <= 4, got.n_kernel_launches   # tau fill, the induction, V0 copy
+    again = engine.lsm_price(ps, 0.05, K, T, 1.0 / n, is_call, p, carry=m.MCP_F32)
+    assert again.price == got.price and again.std_error == got.std_error   # fixed fold order: bitwise reproducible
+    monkeypatch.setenv("MCP_SWEEP_IMPL", "2")
+    ref2 = engine.lsm_price(ps, 0.05, K, T, 1.0 / n, is_call, p, carry=m.MCP_F32, want_first_exercise=True, want_v0=True, want_coeffs=True)
+    assert ref2.n_kernel_launches > n
+    assert abs(got.price - ref2.price) < 3e-7 * ref2.price, (got.price, ref2.price)
+    assert abs(got.std_error - ref2.std_error) < 1e-4 * ref2.std_error + 1e-9 * ref2.price
+    assert np.mean(got.first_exercise == ref2.first_exercise) > 0.9999
+    assert np.max(np.abs(got.v0 - ref2.v0)) < 1e-4 * K
+    if p <= 4:
+        slab = ps.download_timemajor()
+        want = port.lsm_timemajor_f32(slab, 0.05, K, T, 1.0 / n, is_call, p)
+        assert abs(got.price - want["price"]) < 1e-5 * want["price"], (got.price, want["price"])
+        assert np.mean(got.first_exercise == want["first_ex"]) > 0.9999
+    ps.close()
+
+
+def test_lsm_persistent_sweep_is_the_default_for_l2_resident_problems(engine, monkeypatch):
+    monkeypatch.delenv("MCP_SWEEP_IMPL", raising=False)
+    ps = engine.pathset(1 << 20, 16)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.2, 1.0 / 16, seed=2)
+    out = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / 16, False, 3, carry=m.MCP_F32)
+    assert out.n_kernel_launches == 1 and out.n_paths_global == 1 << 20 and 5.5 < out.price < 6.5
+    ps.close()
