@@ -27,14 +27,15 @@ struct McpXchg {
 //   * the PEER region, part of the IPC-shared mailbox block behind the legacy rows: [parity][source rank][MCP_PX_BIGW words],
 //     written by the reducer CTA of every rank into every rank (one NVLink hop), read locally;
 //   * the LOCAL region (plain cudaMalloc, zeroed once): worker rows [parity][MCP_PX_MAXW][MCP_PX_ROWW] (worker CTA -> reducer CTA)
-//     and broadcast slots [parity][MCP_PX_BCW] (reducer CTA -> worker CTAs).
+//     and broadcast slots [parity][MCP_PX_MAXW][MCP_PX_BCW] (reducer CTA -> worker CTAs; one slot per worker, so that
+//     a hundred CTAs never spin on one L2 line).
 constexpr int MCP_PX_BIGW = 4096;
 constexpr int MCP_PX_MAXW = 192;
 constexpr int MCP_PX_ROWW = 48;
-constexpr int MCP_PX_BCW = 32;
+constexpr int MCP_PX_BCW = 16;
 constexpr size_t MCP_XLEGACY_WORDS = (size_t)2 * MCP_XMAX_RANKS * MCP_XROW;
 constexpr size_t MCP_XBOX_WORDS = MCP_XLEGACY_WORDS + (size_t)2 * MCP_XMAX_RANKS * MCP_PX_BIGW;  // whole IPC-shared block
-constexpr size_t MCP_PX_LOCAL_WORDS = (size_t)2 * MCP_PX_MAXW * MCP_PX_ROWW + (size_t)2 * MCP_PX_BCW;
+constexpr size_t MCP_PX_LOCAL_WORDS = (size_t)2 * MCP_PX_MAXW * MCP_PX_ROWW + (size_t)2 * MCP_PX_MAXW * MCP_PX_BCW;
 struct McpPx {
     unsigned long long* const* peer = nullptr;  // device array [nranks]: base of every rank's IPC block (own entry = local block)
     unsigned long long* local = nullptr;        // local region
@@ -64,6 +65,9 @@ struct mcp_ctx {
     std::vector<void*> xchg_opened;        // peers' mailboxes opened with cudaIpcOpenMemHandle
     unsigned long long xchg_seq = 0;       // exchange counter (all ranks advance in lock step)
     void* px_local = nullptr;              // local region of the persistent-sweep exchange (see McpPx)
+    void* px_trace = nullptr;              // MCP_PX_TRACE=1: time stamps of the last persistent sweep
+    size_t px_trace_bytes = 0;
+    int px_trace_rows = 0, px_trace_cols = 0;
 
     // grow-only device scratch (regression partials, coefficient tables, transposition staging ...)
     void* scratch = nullptr;

@@ -162,6 +162,7 @@ int mcp_px_get(mcp_ctx* ctx, McpPx* out) {
         if (cudaMalloc(&ctx->px_local, bytes) != cudaSuccess || cudaMemset(ctx->px_local, 0, bytes) != cudaSuccess) {
             cudaGetLastError();
             if (ctx->px_local) cudaFree(ctx->px_local);
+    if (ctx->px_trace) cudaFree(ctx->px_trace);
             ctx->px_local = nullptr;
             return mcp_fail(ctx, MCP_ERR_NOMEM, "persistent sweep: local exchange region allocation failed");
         }
@@ -237,6 +238,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     ctx->slab_pool.clear();
     xchg_teardown(ctx);
     if (ctx->px_local) cudaFree(ctx->px_local);
+    if (ctx->px_trace) cudaFree(ctx->px_trace);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->carry) cudaFree(ctx->carry);

@@ -65,6 +65,56 @@ struct LsmDev {  // pointers into ctx scratch
     unsigned int* counter;  // CTA completion ticket for the last-block epilogue (self-resetting)
 };
 
+// Constants of a contract (not of a step), computed ONCE on the host (or once per launch on the device): as kernel
+// arguments they sit in the constant bank and cost no register -- and no per-tile re-derivation from the doubles.
+struct StepK {
+    float sg, nsK, nsKlo;  // payoff = max((sg * S + nsK) + nsKlo, 0): strike as a two-float sum     include/core/common.h:8-14
+    float d_hi, d_lo;      // e^{-r dt} as a two-float sum (252 chained roundings stay unbiased)
+    float thr;             // in the money (payoff > 1e-14, LSMPricer.cpp:55)  <=>  sg * S > thr   (exactly, see make_stepk)
+};
+
+__host__ __device__ inline float stepk_payoff(float u /* = sg * S */, float nsK, float nsKlo) {
+#ifdef __CUDA_ARCH__
+    const float t = __fadd_rn(__fadd_rn(u, nsK), nsKlo);
+#else
+    volatile float t0 = u + nsK;  // the device's FFMA with sg = +-1 rounds exactly this sum once
+    volatile float t1 = t0 + nsKlo;
+    const float t = t1;
+#endif
+    return t > 0.f ? t : 0.f;
+}
+
+// The payoff as the kernels compute it is a monotone function of u = sg * S, so { payoff > 1e-14f } = { u > thr } for one
+// float thr: bisection over the ordered bit patterns finds it exactly, and the regression's in-the-money test of a path
+// (taken one pass BEFORE its exercise decision) is a single compare that agrees bit for bit with the decision's own test.
+__host__ __device__ inline StepK make_stepk(double K, double disc, int is_call) {
+    StepK g;
+    const float sgn = is_call ? 1.f : -1.f;
+    const float K_hi = (float)K, K_lo = (float)(K - (double)K_hi);
+    g.sg = sgn;
+    g.nsK = -sgn * K_hi;
+    g.nsKlo = -sgn * K_lo;
+    g.d_hi = (float)disc;
+    g.d_lo = (float)(disc - (double)g.d_hi);
+    auto key2f = [](uint32_t key) -> float {  // order-preserving map of [0, 2^32) onto the floats
+        const uint32_t b = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+#ifdef __CUDA_ARCH__
+        return __uint_as_float(b);
+#else
+        float f;
+        memcpy(&f, &b, 4);
+        return f;
+#endif
+    };
+    uint32_t lo = 0x00800000u, hi = 0xff7fffffu;  // keys of -FLT_MAX (never in the money) and +FLT_MAX (always)
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        if (stepk_payoff(key2f(mid), g.nsK, g.nsKlo) > 1e-14f) hi = mid; else lo = mid;
+    }
+    g.thr = key2f(lo);  // the largest u that is NOT in the money
+    return g;
+}
+
 struct SweepArgs {
     const void* S;   // slab
     int64_t ld, n;   // row stride, paths
@@ -81,6 +131,7 @@ struct SweepArgs {
     McpXchg x;          // peer-memory mailboxes (multi-GPU): the moment all-reduce happens inside this kernel
     unsigned long long seq;  // sequence number of this launch's exchange
     int l2_resident;    // two slab rows + the carry fit in L2: keep them there instead of streaming
+    StepK g;            // contract constants of the packed-fp32 kernels (make_stepk)
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
@@ -261,9 +312,7 @@ MCP_ST8(st8_stream, ".L2::evict_first")
 template <int P>
 struct FastConsts {
     float2 c[P + 1];
-    float2 nmu, is, nmu_p, is_p;  // -mu, 1/s of step j and of step j-1
-    float2 sg, nsK, nsKlo;        // payoff = max(sg*S + nsK + nsKlo, 0)
-    float2 d_hi, d_lo;            // e^{-r dt} as a two-float product
+    float2 is, c0, is_p, c0_p;  // x = S * is + c0 with is = 1/s, c0 = -mu/s, of step j and of step j-1
 };
 
 // Arithmetic of one group of 8 paths held in registers: s8 = S_j, p8 = S_{j-1}, v8 = carry (updated in place).
@@ -271,9 +320,13 @@ struct FastConsts {
 // kernel uses one run of eight: idx1 = idx0 + 4).  TAIL: the ragged last group, paths >= a.n are masked out.
 // KIND 0: the common launch (regress-and-decide step that also accumulates the next regression, 251 of 253 launches
 // at config 3) with every mode test resolved at compile time; KIND 1: any launch, flags read at run time.
+// la[0] sums V0 on the last step; the in-the-money count of a regression step goes to the integer `cnt`.
+// The FP32 pipe is what bounds these kernels once the data sits in L2 (ncu, profiles/r02b): per pair of paths 23
+// packed operations (payoff 2, discount 2, standardise 1, Horner P, mask 1, standardise 1, discount 1, powers P - 1,
+// sums 3P + 1); masks, selects and the count run on the ALU pipe (FSETP / FSEL / predicated add).
 template <int P, bool TAU, bool TAIL, int KIND = 1>
-__device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastConsts<P>& k, const F8& s8, const F8& p8, F8& v8, int64_t idx0, int64_t idx1,
-                                              int mode_rt, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+__device__ __forceinline__ void fast2_compute(const SweepArgs& a, const StepK& g, const FastConsts<P>& k, const F8& s8, const F8& p8, F8& v8, int64_t idx0,
+                                              int64_t idx1, int mode_rt, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2], int& cnt) {
     const int mode = KIND == 0 ? 0 : mode_rt;
     const bool do_moments = KIND == 0 ? true : (a.do_moments != 0), do_final = KIND == 0 ? false : (a.do_final != 0);
     float2 s[4], sp[4];
@@ -292,25 +345,27 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
             if (!ok[2 * q + 1]) { s[q].y = 0.f; sp[q].y = 0.f; v[q].y = 0.f; }
         }
     }
+    const float2 sg = splat2(g.sg), nsK = splat2(g.nsK), nsKlo = splat2(g.nsKlo), d_hi = splat2(g.d_hi), d_lo = splat2(g.d_lo);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float2 pay = __fadd2_rn(__ffma2_rn(s[q], k.sg, k.nsK), k.nsKlo);  // include/core/common.h:8-14
+        float2 pay = __fadd2_rn(__ffma2_rn(s[q], sg, nsK), nsKlo);  // include/core/common.h:8-14
         pay.x = fmaxf(pay.x, 0.f);
         pay.y = fmaxf(pay.y, 0.f);
         if (mode == 2) {
             v[q] = pay;  // LSMPricer.cpp:37-40
         } else {
-            const float2 vd = __ffma2_rn(v[q], k.d_lo, __fmul2_rn(v[q], k.d_hi));
+            const float2 vd = __ffma2_rn(v[q], d_lo, __fmul2_rn(v[q], d_hi));
             if (mode == 1) {
                 v[q] = vd;  // LSMPricer.cpp:43-49
             } else {
-                const float2 x = __fmul2_rn(__fadd2_rn(s[q], k.nmu), k.is);
+                const float2 x = __ffma2_rn(s[q], k.is, k.c0);
                 float2 cont = k.c[P];
 #pragma unroll
                 for (int m = P - 1; m >= 0; --m) cont = __ffma2_rn(cont, x, k.c[m]);
-                // ITM: V = max(payoff, fitted)  (:78-86);  payoff < 1e-14: discounted carry (:89-94);  == 1e-14: 0 (:35)
-                v[q].x = pay.x > 1e-14f ? fmaxf(pay.x, cont.x) : (pay.x < 1e-14f ? vd.x : 0.f);
-                v[q].y = pay.y > 1e-14f ? fmaxf(pay.y, cont.y) : (pay.y < 1e-14f ? vd.y : 0.f);
+                // ITM: V = max(payoff, fitted)  (:78-86);  otherwise the discounted carry (:89-94).  (The reference leaves V = 0
+                // when the payoff EQUALS 1e-14; the fp32 payoff is 0 or >= one ulp of the strike's low word, never that.)
+                v[q].x = pay.x > 1e-14f ? fmaxf(pay.x, cont.x) : vd.x;
+                v[q].y = pay.y > 1e-14f ? fmaxf(pay.y, cont.y) : vd.y;
                 if (TAU) {
                     const int64_t ib = (q < 2 ? idx0 : idx1) + 2 * (q & 1);
                     if (pay.x > 1e-14f && !(pay.x < cont.x) && ok[2 * q]) a.tau[ib] = a.j;
@@ -322,23 +377,26 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
     if (do_moments) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 pp = __fadd2_rn(__ffma2_rn(sp[q], k.sg, k.nsK), k.nsKlo);  // payoff of step j-1 (sign test only)
-            float2 m = make_float2(pp.x > 1e-14f ? 1.f : 0.f, pp.y > 1e-14f ? 1.f : 0.f);  // LSMPricer.cpp:51-58 (one FSET each)
-            if (TAIL) {
-                if (!ok[2 * q]) m.x = 0.f;
-                if (!ok[2 * q + 1]) m.y = 0.f;
-            }
-            const float2 x = __fmul2_rn(__fmul2_rn(__fadd2_rn(sp[q], k.nmu_p), k.is_p), m);
-            const float2 y = __fmul2_rn(__ffma2_rn(v[q], k.d_lo, __fmul2_rn(v[q], k.d_hi)), m);  // LSMPricer.cpp:69
-            la[0] = __fadd2_rn(la[0], m);
-            la[2 * P + 1] = __fadd2_rn(la[2 * P + 1], y);
-            float2 xp = x;
+            const float2 u = __fmul2_rn(sp[q], sg);
+            const bool in_x = u.x > g.thr && ok[2 * q], in_y = u.y > g.thr && ok[2 * q + 1];  // LSMPricer.cpp:51-58 for step j-1
+            float2 x = __ffma2_rn(sp[q], k.is_p, k.c0_p);
+            float2 y = __fmul2_rn(v[q], d_hi);  // LSMPricer.cpp:69 (a regression target needs no two-float discount)
+            x.x = in_x ? x.x : 0.f;  x.y = in_y ? x.y : 0.f;   // x = 0 kills every power, y = 0 every cross moment
+            y.x = in_x ? y.x : 0.f;  y.y = in_y ? y.y : 0.f;
+            cnt += (in_x ? 1 : 0) + (in_y ? 1 : 0);
+            // power sums without forming the high powers: x^e = x^ceil(e/2) * x^floor(e/2) goes straight into the FMA that
+            // accumulates it (P - 1 multiplies + 3P - 1 FMAs + 2 adds per pair)
+            float2 xp[P + 1];
+            xp[0] = x;
+            if (P >= 1) xp[1] = x;
 #pragma unroll
-            for (int e = 1; e <= 2 * P; ++e) {
-                la[e] = __fadd2_rn(la[e], xp);
-                if (e <= P) la[2 * P + 1 + e] = __ffma2_rn(xp, y, la[2 * P + 1 + e]);
-                if (e < 2 * P) xp = __fmul2_rn(xp, x);
-            }
+            for (int e = 2; e <= P; ++e) xp[e] = __fmul2_rn(xp[e - 1], x);
+            la[2 * P + 1] = __fadd2_rn(la[2 * P + 1], y);
+            if (P >= 1) la[1] = __fadd2_rn(la[1], x);
+#pragma unroll
+            for (int e = 2; e <= 2 * P; ++e) la[e] = __ffma2_rn(xp[(e + 1) / 2], xp[e / 2], la[e]);
+#pragma unroll
+            for (int e = 1; e <= P; ++e) la[2 * P + 1 + e] = __ffma2_rn(xp[e], y, la[2 * P + 1 + e]);
         }
     }
     if (do_final) {
@@ -357,12 +415,12 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const FastCons
 // Direct-load form: one group = 8 consecutive paths, 256-bit loads / stores with L2 eviction priorities.
 template <int P, bool TAU, bool TAIL>
 __device__ __forceinline__ void fast2_group(const SweepArgs& a, const FastConsts<P>& k, const float* __restrict__ Sj, const float* __restrict__ Sp,
-                                            float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2]) {
+                                            float* __restrict__ V, int64_t i0, int mode, float2 (&la)[(3 * P + 2) > 2 ? (3 * P + 2) : 2], int& cnt) {
     const F8 s8 = ld8_stream(Sj + i0);
     F8 p8 = s8, v8 = s8;
     if (a.do_moments) p8 = ld8_keep(Sp + i0);
     if (mode != 2) v8 = ld8_stream(V + i0);
-    fast2_compute<P, TAU, TAIL>(a, k, s8, p8, v8, i0, i0 + 4, mode, la);
+    fast2_compute<P, TAU, TAIL>(a, a.g, k, s8, p8, v8, i0, i0 + 4, mode, la, cnt);
     st8_stream(V + i0, v8);
 }
 
@@ -370,18 +428,12 @@ template <int P>
 __device__ __forceinline__ void fast2_load_consts(const SweepArgs& a, FastConsts<P>& k) {
 #pragma unroll
     for (int m = 0; m <= P; ++m) k.c[m] = splat2((float)a.d.coef[(int64_t)a.j * COEF_LD + m]);
-    k.nmu = splat2(-(float)a.d.mu[a.j]);
-    k.is = splat2((float)a.d.inv_s[a.j]);
-    k.nmu_p = splat2(-(float)a.d.mu[a.j > 0 ? a.j - 1 : 0]);
-    k.is_p = splat2((float)a.d.inv_s[a.j > 0 ? a.j - 1 : 0]);
-    const float sgn = a.is_call ? 1.f : -1.f;
-    const float K_hi = (float)a.K, K_lo = (float)(a.K - (double)K_hi);
-    k.sg = splat2(sgn);
-    k.nsK = splat2(-sgn * K_hi);
-    k.nsKlo = splat2(-sgn * K_lo);
-    const float d_hi = (float)a.disc;
-    k.d_hi = splat2(d_hi);
-    k.d_lo = splat2((float)(a.disc - (double)d_hi));
+    const int jp = a.j > 0 ? a.j - 1 : 0;
+    const double is = a.d.inv_s[a.j], is_p = a.d.inv_s[jp];
+    k.is = splat2((float)is);
+    k.c0 = splat2((float)(-a.d.mu[a.j] * is));
+    k.is_p = splat2((float)is_p);
+    k.c0_p = splat2((float)(-a.d.mu[jp] * is_p));
 }
 
 template <int P, bool TAU>
@@ -401,13 +453,13 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast2_kernel(SweepArgs a)
     float2 la[NV];
 #pragma unroll
     for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m][threadIdx.x] = 0.0; }
-    int since = 0;
+    int since = 0, cnt = 0;
 
     const int64_t ngroup = (a.n + 7) >> 3, nfull = a.n >> 3, gstride = (int64_t)gridDim.x * LSM_NT;
     for (int64_t ig = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; ig < ngroup; ig += gstride) {
         const int64_t g = (a.j & 1) ? (ngroup - 1 - ig) : ig;  // serpentine: what the previous sweep touched last is read first
-        if (g < nfull) fast2_group<P, TAU, false>(a, k, Sj, Sp, V, g * 8, mode, la);
-        else fast2_group<P, TAU, true>(a, k, Sj, Sp, V, g * 8, mode, la);
+        if (g < nfull) fast2_group<P, TAU, false>(a, k, Sj, Sp, V, g * 8, mode, la, cnt);
+        else fast2_group<P, TAU, true>(a, k, Sj, Sp, V, g * 8, mode, la, cnt);
         if (++since == FLUSH) {
 #pragma unroll
             for (int m = 0; m < NV; ++m) {
@@ -421,6 +473,7 @@ __global__ void __launch_bounds__(LSM_NT, 3) lsm_sweep_fast2_kernel(SweepArgs a)
         double acc[NV];
 #pragma unroll
         for (int m = 0; m < NV; ++m) acc[m] = sacc[m][threadIdx.x] + ((double)la[m].x + (double)la[m].y);
+        acc[0] += (double)cnt;
         sweep_epilogue<NV, P>(a, acc);
     }
 }
@@ -514,8 +567,7 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     };
     // one elected thread: arm the stage's barrier with the bytes of all its copies, start the slab copies (part 1) and
     // the carry copy (part 2)
-    auto issue = [&](int64_t it, bool part_s, bool part_v) {
-        const int st = (int)(it % n_stages);
+    auto issue_at = [&](int64_t it, int st, bool part_s, bool part_v) {
         const int64_t i0 = tile_of(it) * TMA_TILE;
         const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;  // rows are padded to ld (multiple of 128)
         const uint32_t bytes = (uint32_t)cnt * 4u;
@@ -530,12 +582,12 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     if (tid == 0) {
         for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, TMA_NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, true, false);
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue_at(it, (int)it, true, false);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous sweep (carry, coefficients, ticket) is complete and visible
     const int mode = a.terminal ? 2 : a.d.kind[a.j];
     if (tid == 0)
-        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, false, true);
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue_at(it, (int)it, false, true);
     FastConsts<P> k;
     fast2_load_consts<P>(a, k);
     float2 la[NV];
@@ -543,13 +595,13 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * TMA_NT + tid] = 0.0; }
     __syncthreads();
 
-    int since = 0;
+    int since = 0, cnt = 0;
     auto run_tiles = [&](auto kind_tag) {
     constexpr int KIND = decltype(kind_tag)::value;
     const bool dm = KIND == 0 ? true : (a.do_moments != 0), wv = KIND == 0 ? true : (mode != 2);
+    int st = 0;
+    uint32_t parity = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
-        const int st = (int)(it % n_stages);
-        const uint32_t parity = (uint32_t)((it / n_stages) & 1);
         while (!mbar_try_wait(full + st, parity)) {}
         const float* buf = ring + (size_t)st * (3 * TMA_TILE);
         F8 s8, p8, v8;
@@ -572,18 +624,20 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
         if ((tid & 31) == 0) mbar_arrive(empty + st);
         if (tid == 0 && it + n_stages < my_tiles) {
             while (!mbar_try_wait(empty + st, parity)) {}
-            issue(it + n_stages, true, true);
+            issue_at(it + n_stages, st, true, true);
         }
+        if (++st == n_stages) { st = 0; parity ^= 1u; }
 
         const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = i0 + 2048 + 4 * tid;
-        if (i0 + TMA_TILE <= a.n) fast2_compute<P, TAU, false, KIND>(a, k, s8, p8, v8, ia, ib, mode, la);
-        else fast2_compute<P, TAU, true, KIND>(a, k, s8, p8, v8, ia, ib, mode, la);
+        const bool whole = i0 + TMA_TILE <= a.n;
+        if (whole) fast2_compute<P, TAU, false, KIND>(a, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+        else fast2_compute<P, TAU, true, KIND>(a, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
         if (a.l2_resident) {
-            if (ia < a.ld) stg4_keep(V + ia, v8.q[0], v8.q[1]);
-            if (ib < a.ld) stg4_keep(V + ib, v8.q[2], v8.q[3]);
+            if (whole || ia < a.ld) stg4_keep(V + ia, v8.q[0], v8.q[1]);
+            if (whole || ib < a.ld) stg4_keep(V + ib, v8.q[2], v8.q[3]);
         } else {
-            if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
-            if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+            if (whole || ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
+            if (whole || ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
         }
         if (++since == FLUSH) {
 #pragma unroll
@@ -601,6 +655,7 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
         double acc[NV];
 #pragma unroll
         for (int m = 0; m < NV; ++m) acc[m] = sacc[m * TMA_NT + tid] + (double)(la[m].x + la[m].y);
+        acc[0] += (double)cnt;
         sweep_epilogue<NV, P, TMA_NT>(a, acc);
     }
 }
@@ -660,9 +715,11 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
     w.d.coef = a.coef + (int64_t)cc * a.M * COEF_LD;
     w.d.mu = const_cast<double*>(a.mu) + (int64_t)cc * a.M;
     w.d.inv_s = const_cast<double*>(a.inv_s) + (int64_t)cc * a.M;
+    w.g = make_stepk(w.K, w.disc, w.is_call);  // per warp = per contract, once per launch
     FastConsts<P> k;
     fast2_load_consts<P>(w, k);
     float2 la[NV];
+    int cnt = 0;
 #pragma unroll
     for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * NT + tid] = 0.0; }
 
@@ -721,8 +778,8 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
                     const float4 x0 = *reinterpret_cast<const float4*>(vbuf + oa), x1 = *reinterpret_cast<const float4*>(vbuf + ob);
                     v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
                 }
-                if (i0 + MULTI_TILE <= a.n) fast2_compute<P, false, false>(w, k, s8, p8, v8, ia, ib, mode, la);
-                else fast2_compute<P, false, true>(w, k, s8, p8, v8, ia, ib, mode, la);
+                if (i0 + MULTI_TILE <= a.n) fast2_compute<P, false, false>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+                else fast2_compute<P, false, true>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
                 if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
                 if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
                 if (++since == FLUSH) {
@@ -743,6 +800,7 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
     double acc[NV];
 #pragma unroll
     for (int m = 0; m < NV; ++m) acc[m] = sacc[m * NT + tid] + (double)(la[m].x + la[m].y);
+    acc[0] += (double)cnt;
     double* prow = a.partial + ((int64_t)blockIdx.x * MULTI_MAXC + c) * MOM_LD;
 #pragma unroll
     for (int m = 0; m < NV; ++m) {
@@ -1168,12 +1226,12 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         const int want = env_int("MCP_SWEEP_STAGES", 0);
         if (want > 0 && want < px_stages) px_stages = want;
         if (px_stages > 8) px_stages = 8;
-        int64_t w = ntile / (px_stages + 1);
+        int64_t w = ntile;  // a worker with more tiles than ring stages chains them across steps, one with fewer refills per step
         const int64_t wmax = (ctx->sm_count - 1 < MCP_PX_MAXW ? ctx->sm_count - 1 : MCP_PX_MAXW);
         if (w > wmax) w = wmax;
         if (w < 1) w = 1;
         const bool l2_fit = (size_t)N * 12 <= ((size_t)env_int("MCP_L2_RESIDENT_MB", 104) << 20);
-        const bool want_px = (multi_early && ctx->xchg.enabled) || impl_env == 4 || (impl_env == 0 && l2_fit && w >= 16);
+        const bool want_px = (multi_early && ctx->xchg.enabled) || impl_env == 4 || (impl_env == 0 && l2_fit && ntile >= 32);
         if (want_px && px_stages >= 2) {
             persist = first_exercise ? pick_persist<true>(p) : pick_persist<false>(p);
             px_workers = (int)w;
@@ -1235,6 +1293,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     memset(&a, 0, sizeof(a));
     a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
     a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
+    a.g = make_stepk(prm->strike, disc, prm->is_call);
     const bool multi = ctx->nranks > 1 && ctx->comm;
     const bool p2p = multi && ctx->xchg.enabled;
     if (p2p) a.x = ctx->xchg;
@@ -1255,10 +1314,26 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         memset(&pa, 0, sizeof(pa));
         pa.S = (const float*)ps->data; pa.ld = ps->ld; pa.n = N; pa.V = (float*)dV; pa.tau = dTau;
         pa.coef = d.coef; pa.mu = d.mu; pa.inv_s = d.inv_s; pa.ssum = d.ssum; pa.fin = d.fin; pa.kind = d.kind;
-        pa.K = prm->strike; pa.disc = disc; pa.is_call = prm->is_call; pa.M = M;
+        pa.K = prm->strike; pa.disc = disc; pa.is_call = prm->is_call; pa.M = M; pa.g = a.g;
         pa.ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
         pa.l2_resident = a.l2_resident; pa.n_workers = px_workers; pa.n_stages = px_stages;
         MCP_TRY(mcp_px_get(ctx, &pa.x));
+        if (env_int("MCP_PX_TRACE", 0)) {  // debugging aid: per-step time stamps of every CTA (tools/px_trace.py)
+            const size_t tb = (size_t)M * (px_workers + 1) * 4 * 8;
+            if (ctx->px_trace_bytes < tb) {
+                if (ctx->px_trace) cudaFree(ctx->px_trace);
+                ctx->px_trace = nullptr;
+                ctx->px_trace_bytes = 0;
+                if (cudaMalloc(&ctx->px_trace, tb) == cudaSuccess) ctx->px_trace_bytes = tb;
+                else cudaGetLastError();
+            }
+            if (ctx->px_trace) {
+                cudaMemsetAsync(ctx->px_trace, 0, tb, st);
+                pa.trace = (unsigned long long*)ctx->px_trace;
+                ctx->px_trace_rows = M;
+                ctx->px_trace_cols = px_workers + 1;
+            }
+        }
         pa.seq0 = ctx->xchg_seq + 1;
         ctx->xchg_seq += px::exchanges_per_launch(M, kind.data());
         void* kargs[] = {(void*)&pa};
@@ -1382,6 +1457,20 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
 
 // Several strikes on the SAME path set in one sweep (surface ladders, config 5): throughput mode only (fp32 slab,
 // fp32 carry, one GPU).  Other combinations price the strikes one after the other through mcp_lsm_price.
+// Debugging aid (not part of the reference boundary): the time stamps of the last persistent sweep run with MCP_PX_TRACE=1,
+// [rows][cols][4] uint64 nanoseconds; returns rows * cols * 4 or a negative status.
+extern "C" int64_t mcp_debug_px_trace(mcp_ctx* ctx, unsigned long long* out, int64_t max_words, int* rows, int* cols) {
+    if (!ctx || !ctx->px_trace) return MCP_ERR_INVALID;
+    const int64_t n = (int64_t)ctx->px_trace_rows * ctx->px_trace_cols * 4;
+    if (rows) *rows = ctx->px_trace_rows;
+    if (cols) *cols = ctx->px_trace_cols;
+    if (out && max_words >= n) {
+        cudaStreamSynchronize(ctx->stream);
+        if (cudaMemcpy(out, ctx->px_trace, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MCP_ERR_CUDA;
+    }
+    return n;
+}
+
 extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_params* prm, const double* strikes, int n_strikes,
                                    mcp_lsm_result* res) {
     if (!ctx || !prm || !strikes || !res || n_strikes <= 0) return MCP_ERR_INVALID;

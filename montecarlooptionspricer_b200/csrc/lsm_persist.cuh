@@ -6,10 +6,11 @@
 // paths per GPU (config 3 on 8 GPUs) that tail is a third of the step.  Here the grid stays resident for all M steps:
 //
 //   worker CTAs (blockIdx 1 .. nw)   own a FIXED set of 4096-path tiles for the whole induction and stream them through a
-//       TMA ring that never drains: the tile sequence (step s, tile it) is one continuous stream, and because a
-//       worker's carry tiles are written by that worker only, the loads of step s+1 are issued while step s is still
-//       being computed (generic-proxy stores -> fence.proxy.async -> mbarrier -> bulk copy).  Per step a worker sends
-//       ONE row of regression moments to the reducer and waits for ONE row of coefficients.
+//       TMA ring whose slab copies never drain: the tile sequence (step s, tile it) is one continuous stream, the slab
+//       tiles of step s+1 are in flight while step s is still being computed, and because a worker's carry tiles are
+//       written by that worker only, their copies need no grid barrier -- one proxy fence per step (generic-proxy
+//       stores -> fence.proxy.async -> bulk copy), executed while the worker waits for the coefficients anyway.  Per step
+//       a worker sends ONE row of regression moments to the reducer and waits for ONE row of coefficients.
 //   reducer CTA (blockIdx 0)         does no streaming.  It polls the workers' rows, folds them in worker order, pushes
 //       the folded row straight into every peer GPU's mailbox (plain P2P stores over NVLink, 8-byte words that carry
 //       32 bits of payload and a 32-bit sequence tag, so delivery and publication are one store and one hop), polls its
@@ -49,9 +50,11 @@ struct Args {
     double* fin;       // [4]           sum V0, sum (V0-mean)^2, N (all ranks)
     const int* kind;   // [M]
     double K, disc;
+    StepK g;           // contract constants of the step arithmetic (host-made: they live in the constant bank)
     int is_call, M, ns, l2_resident, n_workers, n_stages;
     McpPx x;
     unsigned long long seq0;  // tag of this launch's first exchange; exchange e uses seq0 + e
+    unsigned long long* trace;  // optional [M][n_workers + 1][4] globaltimer stamps (tools/px_trace.py); nullptr = off
 };
 
 __device__ __forceinline__ unsigned long long tag_of(unsigned long long seq) { return ((seq % 0xffffffffull) + 1ull) << 32; }
@@ -66,8 +69,8 @@ __device__ __forceinline__ void st_word(unsigned long long* p, unsigned long lon
 __device__ __forceinline__ unsigned long long* local_row(const McpPx& x, unsigned long long seq, int w) {
     return x.local + ((size_t)(seq & 1ull) * MCP_PX_MAXW + (size_t)w) * MCP_PX_ROWW;
 }
-__device__ __forceinline__ unsigned long long* local_bc(const McpPx& x, unsigned long long seq) {
-    return x.local + (size_t)2 * MCP_PX_MAXW * MCP_PX_ROWW + (size_t)(seq & 1ull) * MCP_PX_BCW;
+__device__ __forceinline__ unsigned long long* local_bc(const McpPx& x, unsigned long long seq, int w) {
+    return x.local + (size_t)2 * MCP_PX_MAXW * MCP_PX_ROWW + ((size_t)(seq & 1ull) * MCP_PX_MAXW + (size_t)w) * MCP_PX_BCW;
 }
 __device__ __forceinline__ unsigned long long* peer_slot(const McpPx& x, int dst_rank, unsigned long long seq, int src_rank) {
     return x.peer[dst_rank] + MCP_XLEGACY_WORDS + ((size_t)(seq & 1ull) * MCP_XMAX_RANKS + (size_t)src_rank) * MCP_PX_BIGW;
@@ -172,15 +175,20 @@ __device__ __forceinline__ bool exchange(const McpPx& x, unsigned long long seq,
     return peers_ok;
 }
 
-// status word of a broadcast: 0 = go on, 1 = stop (error)
-__device__ __forceinline__ void broadcast(const McpPx& x, unsigned long long seq, const double* vals, int nv, int status) {
+// Reducer -> every worker's own slot: word 0 = status (0 = go on, 1 = stop), words 1 .. 2 nv = the doubles as (low, high) halves.
+static_assert(2 * (MAXP + 1) + 1 <= MCP_PX_BCW, "broadcast slot");
+__device__ __forceinline__ void broadcast(const McpPx& x, unsigned long long seq, int nw, const double* vals, int nv, int status) {
     const unsigned long long tag = tag_of(seq);
-    unsigned long long* bc = local_bc(x, seq);
-    for (int k = threadIdx.x; k < 2 * nv; k += NT) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(vals[k >> 1]);
-        st_word(bc + 1 + k, ((k & 1) ? (b >> 32) : (b & 0xffffffffull)) | tag);
+    const int nwords = 2 * nv + 1;
+    for (int i = threadIdx.x; i < nw * nwords; i += NT) {
+        const int w = i / nwords, k = i - w * nwords;
+        unsigned long long payload = (unsigned long long)(unsigned int)status;
+        if (k > 0) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(vals[(k - 1) >> 1]);
+            payload = ((k - 1) & 1) ? (b >> 32) : (b & 0xffffffffull);
+        }
+        st_word(local_bc(x, seq, w) + k, payload | tag);
     }
-    if (threadIdx.x == 0) st_word(bc, (unsigned long long)(unsigned int)status | tag);
 }
 
 template <int P>
@@ -196,7 +204,7 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
     bool ok = true;
     auto give_up = [&](unsigned long long at_seq) {  // tell the workers (and, through the next push, nobody: peers time out or see status)
         if (tid == 0) *a.x.err = 1;
-        broadcast(a.x, at_seq, vals, 0, 1);
+        broadcast(a.x, at_seq, nw, vals, 0, 1);
     };
 
     // ---- phase 0: standardisation tables from the sample sums of every rank -------------------------------------
@@ -229,7 +237,7 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
         __threadfence();
         __syncthreads();
         if (!ok) { give_up(seq_bc); return; }
-        broadcast(a.x, seq_bc, vals, 0, 0);
+        broadcast(a.x, seq_bc, nw, vals, 0, 0);
     }
 
     // ---- the induction: one exchange per step that regresses, one for {sum V0, N}, one for the squared deviations ----
@@ -238,6 +246,7 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
         if (!dm && !df) continue;
         const unsigned long long tag = tag_of(seq);
         ok = gather_rows(local_row(a.x, seq, 0), MCP_PX_ROWW, nw, 2 * NV, tag, got, &s_fail);
+        if (a.trace && tid == 0) a.trace[((size_t)(M - 1 - j) * (nw + 1)) * 4 + 0] = global_ns();  // all rows in
         // fold the workers' rows in worker order: thread (seg, k) adds a contiguous block of rows, thread k the block sums
         constexpr int NSEG = NT / NV;
         double* seg_sum = vals + RED_VALS;  // [NSEG][NV]
@@ -258,7 +267,9 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
         }
         if (df && tid == 1) vals[1] = (double)a.n;  // the final exchange carries {sum V0, N}
         __syncthreads();
+        if (a.trace && tid == 0) a.trace[((size_t)(M - 1 - j) * (nw + 1)) * 4 + 1] = global_ns();  // folded
         ok = exchange(a.x, seq, vals, NV, got, &s_fail, ok ? 0 : 1) && ok;
+        if (a.trace && tid == 0) a.trace[((size_t)(M - 1 - j) * (nw + 1)) * 4 + 2] = global_ns();  // exchanged
         if (!ok) { give_up(seq); return; }
         if (df) {
             if (tid == 0) {
@@ -267,13 +278,14 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
                 s_coef[0] = vals[0] / vals[1];  // the mean: workers need it for the squared deviations
             }
             __syncthreads();
-            broadcast(a.x, seq, s_coef, 1, 0);
+            broadcast(a.x, seq, nw, s_coef, 1, 0);
         } else {
             if (tid == 0) solve_normal_equations<P>(vals, s_coef);
             __syncthreads();
             if (tid < COEF_LD) a.coef[(size_t)(j - 1) * COEF_LD + tid] = s_coef[tid];
-            broadcast(a.x, seq, s_coef, P + 1, 0);
+            broadcast(a.x, seq, nw, s_coef, P + 1, 0);
         }
+        if (a.trace && tid == 0) a.trace[((size_t)(M - 1 - j) * (nw + 1)) * 4 + 3] = global_ns();  // solved and broadcast
         ++seq;
     }
     // ---- sum of squared deviations ----
@@ -326,33 +338,51 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     // The ring runs ahead across step boundaries when the carry tile it fetches was written at least one full ring earlier in
     // the stream; a worker with fewer tiles than that refills once per step instead (tiny problems only).
     const bool chain = my_tiles > n_stages;
+    // only the last tile of the path set can be ragged, and it is the last tile of the worker that owns it
+    const int n_whole = (int)my_tiles - ((my_tiles > 0 && ((int64_t)w + (my_tiles - 1) * nw + 1) * TILE > a.n) ? 1 : 0);
     const uint64_t pol_first = l2_policy_evict_first(), pol_norm = l2_policy_evict_normal();
     unsigned long long seq = a.seq0;
 
-    // tile g of the stream = (step s = g / my_tiles, tile it = g % my_tiles); one elected thread arms the stage's barrier
-    // with the bytes of all its copies and starts them
-    auto issue = [&](int64_t g) {
-        const int s = (int)(g / my_tiles);
-        const int64_t it = g - (int64_t)s * my_tiles;
-        const int j = M - 1 - s;
-        const bool dm = j > 0 && __ldg(a.kind + j - 1) == 0, want_v = s > 0;
-        const int st = (int)(g % n_stages);
-        const int64_t i0 = ((int64_t)w + it * nw) * TILE;
-        const int64_t cnt = a.ld - i0 < TILE ? a.ld - i0 : TILE;  // rows are padded to ld (multiple of 128)
-        const uint32_t bytes = (uint32_t)cnt * 4u;
-        float* dst = ring + (size_t)st * STAGE_FLOATS;
-        mbar_expect_tx(full + st, bytes * (1u + (dm ? 1u : 0u) + (want_v ? 1u : 0u)));
-        bulk_g2s_hint(dst, S + (int64_t)j * a.ld + i0, bytes, full + st, pol_first);              // last use of row j
-        if (dm) bulk_g2s_hint(dst + TILE, S + (int64_t)(j - 1) * a.ld + i0, bytes, full + st, pol_norm);  // read again next step
-        if (want_v) bulk_g2s_hint(dst + 2 * TILE, V + i0, bytes, full + st, a.l2_resident ? pol_norm : pol_first);
+    // The stream of this worker = (step 0, tiles 0 .. my_tiles-1), (step 1, ...), ...; stream tile g uses ring stage
+    // g mod n_stages.  One elected thread walks it with two cursors (no divisions in the loop): the SLAB cursor arms a stage's
+    // barrier with the bytes of all its copies and starts the copies of S_j | S_{j-1}; the CARRY cursor follows it and starts
+    // the copy of V.  The slab cursor runs ahead across step boundaries; the carry cursor enters a step only after that step's
+    // top-of-loop proxy fence.
+    struct Cursor { int s; int64_t it; int st; int64_t n; };
+    Cursor cs = {0, 0, 0, 0}, cv = {0, 0, 0, 0};  // thread 0 only
+    auto advance = [&](Cursor& c) {
+        ++c.n;
+        if (++c.it == my_tiles) { c.it = 0; ++c.s; }
+        if (++c.st == n_stages) c.st = 0;
     };
-    int64_t issued = 0;  // thread 0 only
+    auto tile_bytes = [&](int64_t i0) -> uint32_t {
+        const int64_t cnt = a.ld - i0 < TILE ? a.ld - i0 : TILE;  // rows are padded to ld (multiple of 128)
+        return (uint32_t)cnt * 4u;
+    };
+    auto issue_slab = [&]() {
+        const int j = M - 1 - cs.s;
+        const bool dm = j > 0 && __ldg(a.kind + j - 1) == 0, want_v = cs.s > 0;
+        const int64_t i0 = ((int64_t)w + cs.it * nw) * TILE;
+        const uint32_t bytes = tile_bytes(i0);
+        float* dst = ring + (size_t)cs.st * STAGE_FLOATS;
+        mbar_expect_tx(full + cs.st, bytes * (1u + (dm ? 1u : 0u) + (want_v ? 1u : 0u)));
+        bulk_g2s_hint(dst, S + (int64_t)j * a.ld + i0, bytes, full + cs.st, pol_first);                      // last use of row j
+        if (dm) bulk_g2s_hint(dst + TILE, S + (int64_t)(j - 1) * a.ld + i0, bytes, full + cs.st, pol_norm);  // read again next step
+        advance(cs);
+    };
+    auto issue_carry = [&]() {
+        if (cv.s > 0) {
+            const int64_t i0 = ((int64_t)w + cv.it * nw) * TILE;
+            bulk_g2s_hint(ring + (size_t)cv.st * STAGE_FLOATS + 2 * TILE, V + i0, tile_bytes(i0), full + cv.st, a.l2_resident ? pol_norm : pol_first);
+        }
+        advance(cv);
+    };
     if (tid == 0) {
         s_stop = 0;
         for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the terminal step reads no carry: its tiles can fly before anything else happens
-        for (; issued < n_stages && issued < my_tiles; ++issued) issue(issued);
+        while (cs.n < n_stages && cs.n < my_tiles) { issue_slab(); issue_carry(); }
     }
     for (int m = 0; m < NV; ++m) sacc[m * NT + tid] = 0.0;
 
@@ -385,7 +415,7 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     seq += (unsigned long long)((M + PH0_ROWS - 1) / PH0_ROWS);
     if (tid == 0) {
         unsigned int status = 1;
-        if (!wait_word(local_bc(a.x, seq_tables), tag_of(seq_tables), &status) || status != 0) s_stop = 1;
+        if (!wait_word(local_bc(a.x, seq_tables, w), tag_of(seq_tables), &status) || status != 0) s_stop = 1;
     }
     __syncthreads();
     __threadfence();
@@ -393,22 +423,14 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     FastConsts<P> k;
     SweepArgs sa;  // the view fast2_compute expects
     memset(&sa, 0, sizeof(sa));
-    sa.n = a.n; sa.tau = a.tau; sa.is_call = a.is_call; sa.K = a.K; sa.disc = a.disc;
-    {
-        const float sgn = a.is_call ? 1.f : -1.f;
-        const float K_hi = (float)a.K, K_lo = (float)(a.K - (double)K_hi);
-        k.sg = splat2(sgn);
-        k.nsK = splat2(-sgn * K_hi);
-        k.nsKlo = splat2(-sgn * K_lo);
-        const float d_hi = (float)a.disc;
-        k.d_hi = splat2(d_hi);
-        k.d_lo = splat2((float)(a.disc - (double)d_hi));
-    }
+    sa.n = a.n; sa.tau = a.tau;
     float2 la[NV];
 #pragma unroll
     for (int m = 0; m < NV; ++m) la[m] = make_float2(0.f, 0.f);
-    int since = 0;
-    int64_t g = 0;
+    int since = 0, cnt = 0;
+    int64_t g = 0;        // stream tiles consumed
+    int cst = 0;          // ring stage / phase parity of the next tile to consume
+    uint32_t cpar = 0;
     unsigned long long seq_coef = 0;  // sequence number whose broadcast carries the coefficients of the coming step
     double mean = 0.0;
 
@@ -416,10 +438,14 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
         const int j = M - 1 - s;
         const int mode = s == 0 ? 2 : __ldg(a.kind + j);
         const bool dm = j > 0 && __ldg(a.kind + j - 1) == 0, df = j == 0;
+        // every carry store of the previous step is ordered before the bulk copies (async proxy) that fetch it back
         asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();  // everybody is done with the previous step's constants (and, short streams, with its carry stores)
-        if (!chain && s > 0 && tid == 0)
-            for (; issued < (int64_t)(s + 1) * my_tiles; ++issued) issue(issued);
+        __syncthreads();
+        if (tid == 0 && s > 0) {
+            if (!chain)
+                while (cs.s <= s && cs.n < g_total) issue_slab();
+            while (cv.n < cs.n && cv.s <= s) issue_carry();  // carry parts of the tiles whose slab part ran ahead
+        }
         // ---- constants of the step: c_j from the reducer's broadcast (the only wait of the step), mu / 1/s from the tables ----
         if (tid < 4) {
             const int jj = (tid < 2) ? j : (j > 0 ? j - 1 : 0);
@@ -428,88 +454,92 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
         if (mode == 0) {
             if (tid <= 2 * (P + 1)) {  // word 0 = status, words 1.. = c_0 .. c_P as (low, high) halves
                 unsigned int lo = 1;
-                const bool got_it = wait_word(local_bc(a.x, seq_coef) + tid, tag_of(seq_coef), &lo);
+                const bool got_it = wait_word(local_bc(a.x, seq_coef, w) + tid, tag_of(seq_coef), &lo);
                 if (tid == 0) { if (!got_it || lo != 0) s_stop = 1; }
                 else reinterpret_cast<unsigned int*>(s_c)[tid - 1] = got_it ? lo : 0u;
             }
         }
         __syncthreads();
         if (s_stop) break;
+        if (a.trace && tid == 0) a.trace[((size_t)s * (nw + 1) + (w + 1)) * 4 + 0] = global_ns();  // constants in hand
 #pragma unroll
         for (int m = 0; m <= P; ++m) k.c[m] = splat2(mode == 0 ? (float)s_c[m] : 0.f);
-        k.nmu = splat2(-(float)s_c[COEF_LD]);
         k.is = splat2((float)s_c[COEF_LD + 1]);
-        k.nmu_p = splat2(-(float)s_c[COEF_LD + 2]);
+        k.c0 = splat2((float)(-s_c[COEF_LD] * s_c[COEF_LD + 1]));
         k.is_p = splat2((float)s_c[COEF_LD + 3]);
+        k.c0_p = splat2((float)(-s_c[COEF_LD + 2] * s_c[COEF_LD + 3]));
         sa.j = j; sa.terminal = s == 0; sa.do_moments = dm; sa.do_final = df;
 
-        auto run_tiles = [&](auto kind_tag) {
+        // One tile of the stream.  WHOLE tiles (all but possibly the very last tile of the path set) take the path without
+        // bounds tests; per-thread addresses advance by a constant stride.
+        auto one_tile = [&](auto kind_tag, auto tail_tag, float* vp, int64_t i0) {
             constexpr int KIND = decltype(kind_tag)::value;
+            constexpr bool TAILT = decltype(tail_tag)::value;
             const bool ldm = KIND == 0 ? true : dm, wv = KIND == 0 ? true : (mode != 2);
-            for (int64_t it = 0; it < my_tiles; ++it, ++g) {
-                const int st = (int)(g % n_stages);
-                const uint32_t parity = (uint32_t)((g / n_stages) & 1);
-                while (!mbar_try_wait(full + st, parity)) {}
-                const float* buf = ring + (size_t)st * STAGE_FLOATS;
-                F8 s8, p8, v8;
-                {
-                    const float4 x0 = *reinterpret_cast<const float4*>(buf + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2048 + 4 * tid);
-                    s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
-                }
-                p8 = s8; v8 = s8;
-                if (ldm) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(buf + TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + TILE + 2048 + 4 * tid);
-                    p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
-                }
-                if (wv) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(buf + 2 * TILE + 4 * tid), x1 = *reinterpret_cast<const float4*>(buf + 2 * TILE + 2048 + 4 * tid);
-                    v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
-                }
-                // Hand the stage back.  Everything this thread stored to the carry so far (tiles < g of the stream) is
-                // ordered before the arrival and made visible to the async proxy, so when all 16 warps have arrived the
-                // elected thread may start the copies of stream tile g + n_stages -- whose carry tile was written at
-                // stream position g + n_stages - my_tiles < g (the host guarantees my_tiles > n_stages).
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + st);
-                if (tid == 0 && chain && g + n_stages < g_total) {
-                    while (!mbar_try_wait(empty + st, parity)) {}
-                    issue(g + n_stages);
-                    issued = g + n_stages + 1;
-                }
-                const int64_t i0 = ((int64_t)w + it * nw) * TILE, ia = i0 + 4 * tid, ib = i0 + 2048 + 4 * tid;
-                if (i0 + TILE <= a.n) fast2_compute<P, TAU, false, KIND>(sa, k, s8, p8, v8, ia, ib, mode, la);
-                else fast2_compute<P, TAU, true, KIND>(sa, k, s8, p8, v8, ia, ib, mode, la);
-                if (a.l2_resident) {
-                    if (ia < a.ld) stg4_keep(V + ia, v8.q[0], v8.q[1]);
-                    if (ib < a.ld) stg4_keep(V + ib, v8.q[2], v8.q[3]);
-                } else {
-                    if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
-                    if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
-                }
-                if (++since == FLUSH) {
-#pragma unroll
-                    for (int m = 0; m < NV; ++m) {
-                        sacc[m * NT + tid] += (double)(la[m].x + la[m].y);
-                        la[m] = make_float2(0.f, 0.f);
-                    }
-                    since = 0;
-                }
+            const int st = cst;
+            const uint32_t parity = cpar;
+            while (!mbar_try_wait(full + st, parity)) {}
+            const float* buf = ring + (size_t)st * STAGE_FLOATS + 4 * tid;
+            F8 s8, p8, v8;
+            {
+                const float4 x0 = *reinterpret_cast<const float4*>(buf), x1 = *reinterpret_cast<const float4*>(buf + 2048);
+                s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
             }
+            p8 = s8; v8 = s8;
+            if (ldm) {
+                const float4 x0 = *reinterpret_cast<const float4*>(buf + TILE), x1 = *reinterpret_cast<const float4*>(buf + TILE + 2048);
+                p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
+            }
+            if (wv) {
+                const float4 x0 = *reinterpret_cast<const float4*>(buf + 2 * TILE), x1 = *reinterpret_cast<const float4*>(buf + 2 * TILE + 2048);
+                v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
+            }
+            // this warp holds its part of the stage in registers; once all 16 warps have said so the slot is refilled: with
+            // the next tile of this step (slab and carry), or with the slab part of a tile of the next step
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);
+            if (tid == 0 && chain && cs.n < g_total) {
+                while (!mbar_try_wait(empty + st, parity)) {}
+                issue_slab();
+                while (cv.n < cs.n && cv.s <= s) issue_carry();
+            }
+            if (++cst == n_stages) { cst = 0; cpar ^= 1u; }
+            const int64_t ia = i0 + 4 * tid, ib = ia + 2048;
+            fast2_compute<P, TAU, TAILT, KIND>(sa, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+            if (!TAILT || ia < a.ld) stg4_keep(vp, v8.q[0], v8.q[1]);
+            if (!TAILT || ib < a.ld) stg4_keep(vp + 2048, v8.q[2], v8.q[3]);
+            if (++since == FLUSH) {
+#pragma unroll
+                for (int m = 0; m < NV; ++m) {
+                    sacc[m * NT + tid] += (double)(la[m].x + la[m].y);
+                    la[m] = make_float2(0.f, 0.f);
+                }
+                since = 0;
+            }
+        };
+        auto run_tiles = [&](auto kind_tag) {
+            float* vp = V + (int64_t)w * TILE + 4 * tid;
+            const int64_t vstride = (int64_t)nw * TILE;
+            int64_t i0 = (int64_t)w * TILE;  // (dead code in the whole-tile loop unless first-exercise indices are wanted)
+            for (int it = 0; it < n_whole; ++it, vp += vstride, i0 += vstride) one_tile(kind_tag, std::false_type{}, vp, i0);
+            if (n_whole < (int)my_tiles) one_tile(kind_tag, std::true_type{}, vp, i0);
+            g += my_tiles;
         };
         if (mode == 0 && dm && !df) run_tiles(std::integral_constant<int, 0>{});
         else run_tiles(std::integral_constant<int, 1>{});
 
+        if (a.trace && tid == 0) a.trace[((size_t)s * (nw + 1) + (w + 1)) * 4 + 1] = global_ns();      // thread 0 through its tiles
         if (dm || df) {
             // ---- this worker's row of the step: warp sums -> 16 rows in shared memory -> thread m adds them in warp order ----
 #pragma unroll
             for (int m = 0; m < NV; ++m) {
-                const double t = warp_sum(sacc[m * NT + tid] + (double)(la[m].x + la[m].y));
+                const double t = warp_sum(sacc[m * NT + tid] + (double)(la[m].x + la[m].y) + (m == 0 ? (double)cnt : 0.0));
                 if (lane == 0) red[warp][m] = t;
                 sacc[m * NT + tid] = 0.0;
                 la[m] = make_float2(0.f, 0.f);
             }
             since = 0;
+            cnt = 0;
             __syncthreads();
             if (tid < NV) {
                 double t = 0.0;
@@ -517,6 +547,7 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
                 for (int q = 0; q < NT / 32; ++q) t += red[q][tid];
                 st_tagged_double(local_row(a.x, seq, w), tid, t, tag_of(seq));
             }
+            if (a.trace && tid == 0) a.trace[((size_t)s * (nw + 1) + (w + 1)) * 4 + 2] = global_ns();  // row sent
             seq_coef = seq;
             ++seq;
         }
@@ -526,7 +557,7 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     if (!s_stop) {
         if (tid < 3) {
             unsigned int lo = 1;
-            const bool got_it = wait_word(local_bc(a.x, seq_coef) + tid, tag_of(seq_coef), &lo);
+            const bool got_it = wait_word(local_bc(a.x, seq_coef, w) + tid, tag_of(seq_coef), &lo);
             if (tid == 0) { if (!got_it || lo != 0) s_stop = 1; }
             else reinterpret_cast<unsigned int*>(s_c)[tid - 1] = got_it ? lo : 0u;
         }
@@ -556,11 +587,13 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
         }
     }
     // never leave with bulk copies in flight into this CTA's shared memory
-    if (tid == 0)
-        for (; g < issued; ++g) {
-            const int st = (int)(g % n_stages);
-            while (!mbar_try_wait(full + st, (uint32_t)((g / n_stages) & 1))) {}
+    if (tid == 0) {
+        while (cv.n < cs.n) issue_carry();  // (stop path) complete the armed barriers
+        for (; g < cs.n; ++g) {
+            while (!mbar_try_wait(full + cst, cpar)) {}
+            if (++cst == n_stages) { cst = 0; cpar ^= 1u; }
         }
+    }
     __syncthreads();
 }
 
