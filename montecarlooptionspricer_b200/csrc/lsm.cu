@@ -69,8 +69,10 @@ struct LsmDev {  // pointers into ctx scratch
 // arguments they sit in the constant bank and cost no register -- and no per-tile re-derivation from the doubles.
 struct StepK {
     float sg, nsK, nsKlo;  // payoff = max((sg * S + nsK) + nsKlo, 0): strike as a two-float sum     include/core/common.h:8-14
-    float d_hi, d_lo;      // e^{-r dt} as a two-float sum (252 chained roundings stay unbiased)
-    float thr;             // in the money (payoff > 1e-14, LSMPricer.cpp:55)  <=>  sg * S > thr   (exactly, see make_stepk)
+    float ne1;             // -(1 - e^{-r dt}): V e^{-r dt} = fma(V, ne1, V), ONE operation, correctly rounded for a factor that is
+                           // within 1.2e-11 of the true one (1 - e^{-r dt} ~ 2e-4 keeps 24 bits of its own)
+    float thrS;            // in the money (payoff > 1e-14, LSMPricer.cpp:55)  <=>  (S > thrS) != flip   (exactly, see make_stepk)
+    int flip;              // 1 for puts
 };
 
 __host__ __device__ inline float stepk_payoff(float u /* = sg * S */, float nsK, float nsKlo) {
@@ -94,8 +96,7 @@ __host__ __device__ inline StepK make_stepk(double K, double disc, int is_call) 
     g.sg = sgn;
     g.nsK = -sgn * K_hi;
     g.nsKlo = -sgn * K_lo;
-    g.d_hi = (float)disc;
-    g.d_lo = (float)(disc - (double)g.d_hi);
+    g.ne1 = -(float)(1.0 - disc);
     auto key2f = [](uint32_t key) -> float {  // order-preserving map of [0, 2^32) onto the floats
         const uint32_t b = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
 #ifdef __CUDA_ARCH__
@@ -111,7 +112,10 @@ __host__ __device__ inline StepK make_stepk(double K, double disc, int is_call) 
         const uint32_t mid = lo + (hi - lo) / 2u;
         if (stepk_payoff(key2f(mid), g.nsK, g.nsKlo) > 1e-14f) hi = mid; else lo = mid;
     }
-    g.thr = key2f(lo);  // the largest u that is NOT in the money
+    // lo = key of the largest u = sg * S that is NOT in the money.  Calls (u = S): ITM <=> S > u_lo.  Puts (u = -S): ITM <=>
+    // -S > u_lo <=> S < -u_lo <=> not (S > pred(-u_lo)), and pred(-u) = -(succ(u)) = -key2f(hi).
+    g.flip = is_call ? 0 : 1;
+    g.thrS = is_call ? key2f(lo) : -key2f(hi);
     return g;
 }
 
@@ -320,7 +324,7 @@ struct FastConsts {
 // kernel uses one run of eight: idx1 = idx0 + 4).  TAIL: the ragged last group, paths >= a.n are masked out.
 // KIND 0: the common launch (regress-and-decide step that also accumulates the next regression, 251 of 253 launches
 // at config 3) with every mode test resolved at compile time; KIND 1: any launch, flags read at run time.
-// la[0] sums V0 on the last step; the in-the-money count of a regression step goes to the integer `cnt`.
+// la[0] counts the in-the-money paths of a regression step and sums V0 on the last step (`cnt` is a spare integer counter).
 // The FP32 pipe is what bounds these kernels once the data sits in L2 (ncu, profiles/r02b): per pair of paths 23
 // packed operations (payoff 2, discount 2, standardise 1, Horner P, mask 1, standardise 1, discount 1, powers P - 1,
 // sums 3P + 1); masks, selects and the count run on the ALU pipe (FSETP / FSEL / predicated add).
@@ -345,16 +349,18 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const StepK& g
             if (!ok[2 * q + 1]) { s[q].y = 0.f; sp[q].y = 0.f; v[q].y = 0.f; }
         }
     }
-    const float2 sg = splat2(g.sg), nsK = splat2(g.nsK), nsKlo = splat2(g.nsKlo), d_hi = splat2(g.d_hi), d_lo = splat2(g.d_lo);
+    const float2 sg = splat2(g.sg), nsK = splat2(g.nsK), nsKlo = splat2(g.nsKlo), ne1 = splat2(g.ne1);
+    const bool flip = g.flip != 0, klo = g.nsKlo != 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float2 pay = __fadd2_rn(__ffma2_rn(s[q], sg, nsK), nsKlo);  // include/core/common.h:8-14
+        float2 pay = __ffma2_rn(s[q], sg, nsK);  // include/core/common.h:8-14
+        if (klo) pay = __fadd2_rn(pay, nsKlo);   // (strikes that are exact in fp32 have no low word)
         pay.x = fmaxf(pay.x, 0.f);
         pay.y = fmaxf(pay.y, 0.f);
         if (mode == 2) {
             v[q] = pay;  // LSMPricer.cpp:37-40
         } else {
-            const float2 vd = __ffma2_rn(v[q], d_lo, __fmul2_rn(v[q], d_hi));
+            const float2 vd = __ffma2_rn(v[q], ne1, v[q]);
             if (mode == 1) {
                 v[q] = vd;  // LSMPricer.cpp:43-49
             } else {
@@ -377,13 +383,13 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const StepK& g
     if (do_moments) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 u = __fmul2_rn(sp[q], sg);
-            const bool in_x = u.x > g.thr && ok[2 * q], in_y = u.y > g.thr && ok[2 * q + 1];  // LSMPricer.cpp:51-58 for step j-1
+            // LSMPricer.cpp:51-58 for step j-1: one compare per path on the ALU pipe (the FP32 pipe is the busy one)
+            const bool in_x = ((sp[q].x > g.thrS) != flip) && ok[2 * q], in_y = ((sp[q].y > g.thrS) != flip) && ok[2 * q + 1];
             float2 x = __ffma2_rn(sp[q], k.is_p, k.c0_p);
-            float2 y = __fmul2_rn(v[q], d_hi);  // LSMPricer.cpp:69 (a regression target needs no two-float discount)
+            float2 y = __ffma2_rn(v[q], ne1, v[q]);  // LSMPricer.cpp:69
             x.x = in_x ? x.x : 0.f;  x.y = in_y ? x.y : 0.f;   // x = 0 kills every power, y = 0 every cross moment
             y.x = in_x ? y.x : 0.f;  y.y = in_y ? y.y : 0.f;
-            cnt += (in_x ? 1 : 0) + (in_y ? 1 : 0);
+            la[0] = __fadd2_rn(la[0], make_float2(in_x ? 1.f : 0.f, in_y ? 1.f : 0.f));
             // power sums without forming the high powers: x^e = x^ceil(e/2) * x^floor(e/2) goes straight into the FMA that
             // accumulates it (P - 1 multiplies + 3P - 1 FMAs + 2 adds per pair)
             float2 xp[P + 1];
