@@ -667,6 +667,169 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// sweep(j), PARITY arithmetic on the TMA ring (fp32 slab, fp64 carry): every decision and every moment in fp64 on the
+// stored values -- the arithmetic of lsm_sweep_kernel, bit for bit per path -- but fed like the throughput kernel: one
+// persistent 512-thread CTA per SM, tiles of S_j | S_{j-1} (fp32) | V (fp64) = 64 KB per 4096 paths through a three-stage
+// ring of bulk async copies, programmatic dependent launch.  The grid-stride parity kernel ran at 0.48 of the 20 B/path-step
+// roofline (long-scoreboard stalls: not enough bytes in flight at 24 warps/SM); the DFMA work (~25 per path-step) is a
+// third of the HBM time on B200, so this kernel is HBM-bound.  Moments stay in per-thread fp64 registers.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TMA64_STAGE_BYTES = (2 * 4 + 8) * TMA_TILE;  // S_j | S_{j-1} | V(double)
+
+__device__ __forceinline__ void stg2d_stream(double* p, double a, double b) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+template <int P>
+__global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma64_kernel(SweepArgs a, int n_stages) {
+    constexpr int NM = 3 * P + 2;
+    constexpr int NV = NM > 2 ? NM : 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * TMA64_STAGE_BYTES);
+    uint64_t* empty = full + 8;
+    const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
+    const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
+    double* __restrict__ V = reinterpret_cast<double*>(a.V);
+    const int tid = threadIdx.x;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int64_t ntile = (a.n + TMA_TILE - 1) / TMA_TILE;
+    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint64_t pol = a.l2_resident ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const bool want_v = !a.terminal;
+    auto tile_of = [&](int64_t it) -> int64_t {
+        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
+        return (a.j & 1) ? (ntile - 1 - t) : t;
+    };
+    auto issue_at = [&](int64_t it, int st, bool part_s, bool part_v) {
+        const int64_t i0 = tile_of(it) * TMA_TILE;
+        const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        unsigned char* dst = smem_raw + (size_t)st * TMA64_STAGE_BYTES;
+        if (part_s) {
+            mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (want_v ? 2u : 0u)));
+            bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
+            if (a.do_moments) bulk_g2s(dst + 4 * TMA_TILE, Sp + i0, bytes, full + st);
+        }
+        if (part_v && want_v) bulk_g2s_hint(dst + 8 * TMA_TILE, V + i0, 2u * bytes, full + st, pol);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, TMA_NT / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue_at(it, (int)it, true, false);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int mode = a.terminal ? 2 : a.d.kind[a.j];  // 0 regress/decide, 1 discount only, 2 terminal payoff
+    if (tid == 0)
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue_at(it, (int)it, false, true);
+    double c[P + 1];
+#pragma unroll
+    for (int k = 0; k <= P; ++k) c[k] = a.d.coef[(int64_t)a.j * COEF_LD + k];
+    const double mu = a.d.mu[a.j], inv_s = a.d.inv_s[a.j];
+    const double mu_p = a.d.mu[a.j > 0 ? a.j - 1 : 0], inv_s_p = a.d.inv_s[a.j > 0 ? a.j - 1 : 0];
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    int cnt = 0;
+    __syncthreads();
+
+    int st = 0;
+    uint32_t parity = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        while (!mbar_try_wait(full + st, parity)) {}
+        const unsigned char* buf = smem_raw + (size_t)st * TMA64_STAGE_BYTES;
+        // thread t owns paths [4t, 4t+4) and [2048 + 4t, 2048 + 4t + 4) of the tile
+        float4 sA = *reinterpret_cast<const float4*>(buf + 16 * tid), sB = *reinterpret_cast<const float4*>(buf + 8192 + 16 * tid);
+        float4 pA = sA, pB = sB;
+        if (a.do_moments) {
+            pA = *reinterpret_cast<const float4*>(buf + 4 * TMA_TILE + 16 * tid);
+            pB = *reinterpret_cast<const float4*>(buf + 4 * TMA_TILE + 8192 + 16 * tid);
+        }
+        double v[8];
+        if (mode != 2) {
+            const double2* vb = reinterpret_cast<const double2*>(buf + 8 * TMA_TILE);
+            const double2 v0 = vb[2 * tid], v1 = vb[2 * tid + 1], v2 = vb[1024 + 2 * tid], v3 = vb[1024 + 2 * tid + 1];
+            v[0] = v0.x; v[1] = v0.y; v[2] = v1.x; v[3] = v1.y; v[4] = v2.x; v[5] = v2.y; v[6] = v3.x; v[7] = v3.y;
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + st);
+        if (tid == 0 && it + n_stages < my_tiles) {
+            while (!mbar_try_wait(empty + st, parity)) {}
+            issue_at(it + n_stages, st, true, true);
+        }
+        if (++st == n_stages) { st = 0; parity ^= 1u; }
+
+        const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = ia + 2048;
+        const float sv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+        const float pv[8] = {pA.x, pA.y, pA.z, pA.w, pB.x, pB.y, pB.z, pB.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t i = (e < 4 ? ia : ib) + (e & 3);
+            const bool live = i < a.n;
+            const double s = f2d(sv[e]);
+            const double pay = payoff_fn(a.is_call, s, a.K);
+            if (mode == 2) {
+                v[e] = pay;  // LSMPricer.cpp:37-40
+            } else if (mode == 1) {
+                v[e] = v[e] * a.disc;  // LSMPricer.cpp:43-49
+            } else {
+                const double x = (s - mu) * inv_s;
+                double cont = c[P];
+#pragma unroll
+                for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
+                const bool itm = pay > 1e-14;   // LSMPricer.cpp:55
+                const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate (LSMPricer.cpp:85)
+                const double carried = pay < 1e-14 ? v[e] * a.disc : 0.0;  // LSMPricer.cpp:89-94; == 1e-14 keeps the initial 0 (:35)
+                v[e] = itm ? (ex ? pay : cont) : carried;
+                if (a.tau && itm && ex && live) a.tau[i] = a.j;
+            }
+            if (!live) v[e] = 0.0;  // pad lanes: never NaN / Inf in the carry
+        }
+        if (ia < a.ld) { stg2d_stream(V + ia, v[0], v[1]); stg2d_stream(V + ia + 2, v[2], v[3]); }
+        if (ib < a.ld) { stg2d_stream(V + ib, v[4], v[5]); stg2d_stream(V + ib + 2, v[6], v[7]); }
+        if (a.do_moments) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int64_t i = (e < 4 ? ia : ib) + (e & 3);
+                const double sp = f2d(pv[e]);
+                if (i < a.n && payoff_fn(a.is_call, sp, a.K) > 1e-14) {  // LSMPricer.cpp:51-58 for step j-1
+                    const double x = (sp - mu_p) * inv_s_p, y = v[e] * a.disc;  // LSMPricer.cpp:69
+                    double xp = x;
+                    ++cnt;
+                    acc[2 * P + 1] += y;
+#pragma unroll
+                    for (int k = 1; k <= 2 * P; ++k) {
+                        acc[k] += xp;
+                        if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
+                        if (k < 2 * P) xp *= x;
+                    }
+                }
+            }
+        }
+        if (a.do_final) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if ((e < 4 ? ia : ib) + (e & 3) < a.n) acc[0] += v[e];
+        }
+    }
+    if (a.do_moments) acc[0] = (double)cnt;
+    if (a.do_moments || a.do_final) sweep_epilogue<NV, P, TMA_NT>(a, acc);
+}
+
+typedef void (*SweepFn2Fwd)(SweepArgs, int);
+inline SweepFn2Fwd pick_sweep_tma64(int p) {
+    switch (p) {
+        case 0: return lsm_sweep_tma64_kernel<0>;
+        case 1: return lsm_sweep_tma64_kernel<1>;
+        case 2: return lsm_sweep_tma64_kernel<2>;
+        case 3: return lsm_sweep_tma64_kernel<3>;
+        case 4: return lsm_sweep_tma64_kernel<4>;
+        case 5: return lsm_sweep_tma64_kernel<5>;
+        default: return lsm_sweep_tma64_kernel<6>;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // sweep(j) for SEVERAL CONTRACTS ON THE SAME PATHS (strike ladder of a surface, BASELINE config 5): one warp per
 // contract.  The slab tiles S_j | S_{j-1} are fetched once per CTA by the TMA ring and read by all warps from shared
 // memory; the ring also carries every contract's carry tile, each consumed by its own warp.  Per path-step that is 8 B of slab + 8 B of carry per
@@ -1203,6 +1366,18 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     int tma_stages = 0;
     size_t tma_smem = 0;
     const int64_t ntile = (N + TMA_TILE - 1) / TMA_TILE;
+    if (ps->dtype == MCP_F32 && carry == MCP_F64 && !small && env_int("MCP_SWEEP64_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
+        // parity arithmetic on the TMA ring: 64 KB stages (S_j | S_{j-1} | fp64 V), moments in registers
+        tma_stages = (int)((227u * 1024u - 12288u - 128u) / TMA64_STAGE_BYTES);
+        const int want = env_int("MCP_SWEEP_STAGES", 0);
+        if (want > 0 && want < tma_stages) tma_stages = want;
+        if (tma_stages >= 2) {
+            sweep_tma = pick_sweep_tma64(p);
+            tma_smem = (size_t)tma_stages * TMA64_STAGE_BYTES + 128;
+            MCP_TRY(mcp_kernel_config(ctx, (const void*)sweep_tma, TMA_NT, tma_smem, nullptr));
+            grid = ctx->sm_count < ntile ? ctx->sm_count : ntile;
+        }
+    }
     if (ps->dtype == MCP_F32 && carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
         const size_t fixed = 128 + (size_t)nv * TMA_NT * 8;

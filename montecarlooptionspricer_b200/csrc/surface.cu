@@ -25,6 +25,15 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
     MCP_CUDA(ctx, cudaEventCreate(&e0));
     MCP_CUDA(ctx, cudaEventCreate(&e1));
     int rc = MCP_OK;
+    // ONE slab, sized for the longest maturity this call owns, serves every maturity (row j of the time-major slab is the
+    // same memory whatever the number of rows in use): no 4 GB cudaMalloc / cudaFree pair per maturity
+    int n_steps_max = 0;
+    for (int mi = mat_first; mi < n_maturities; mi += mat_stride) {
+        const int n_steps = (int)floor(maturities[mi] * (double)steps_per_year);
+        if (n_steps > n_steps_max) n_steps_max = n_steps;
+    }
+    mcp_pathset* ps = nullptr;
+    if (n_steps_max >= 1) rc = mcp_pathset_create(ctx, n_paths, n_steps_max, MCP_F32, &ps);
     for (int mi = mat_first; mi < n_maturities && rc == MCP_OK; mi += mat_stride) {
         const double T = maturities[mi];
         const int n_steps = (int)floor(T * (double)steps_per_year);  // PredictionGen.cpp:718
@@ -35,9 +44,7 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
             }
             continue;
         }
-        mcp_pathset* ps = nullptr;
-        rc = mcp_pathset_create(ctx, n_paths, n_steps, MCP_F32, &ps);
-        if (rc != MCP_OK) break;
+        ps->n_steps = n_steps;  // a view of the first n_steps + 1 rows
         cudaEventRecord(e0, ctx->stream);
         rc = mcp_gen_rbergomi(ctx, ps, model, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(mi + 1), path_offset, nullptr, nullptr);
         cudaEventRecord(e1, ctx->stream);
@@ -57,6 +64,9 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) gen_total += ms;
         }
+    }
+    if (ps) {
+        ps->n_steps = n_steps_max;
         mcp_pathset_destroy(ps);
     }
     cudaEventDestroy(e0);

@@ -335,3 +335,26 @@ def test_lsm_persistent_sweep_is_the_default_for_l2_resident_problems(engine, mo
     out = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / 16, False, 3, carry=m.MCP_F32)
     assert out.n_kernel_launches == 1 and out.n_paths_global == 1 << 20 and 5.5 < out.price < 6.5
     ps.close()
+
+
+def test_lsm_parity_arithmetic_on_the_tma_ring_is_bit_exact(engine, port, monkeypatch):
+    """The fp64-carry sweep fed by the TMA ring (>= 2 tiles of 4096 paths per SM) takes the same decisions as the
+    grid-stride parity kernel and as the oracle: exercise indices bit-exact, price to 1e-9; ragged path count, put and call."""
+    n_paths, n = 2 * 148 * 4096 + 4096 * 3 + 77, 12
+    ps = engine.pathset(n_paths, n)
+    engine.gen_gbm(ps, 100.0, 0.05, 0.2, 1.0 / n, seed=25)
+    slab = ps.download_timemajor()
+    _poison_padding(ps)
+    for is_call, K, p in ((False, 100.0, 3), (True, 97.0, 2)):
+        want = port.lsm_timemajor_f32(slab, 0.05, K, 1.0, 1.0 / n, is_call, p)
+        got = {}
+        for impl in ("3", "0"):
+            monkeypatch.setenv("MCP_SWEEP64_IMPL", impl)
+            got[impl] = engine.lsm_price(ps, 0.05, K, 1.0, 1.0 / n, is_call, p, carry=m.MCP_F64, want_first_exercise=True, want_v0=True)
+            assert abs(got[impl].price - want["price"]) <= 1e-9 * want["price"], (impl, got[impl].price, want["price"])
+            mism = np.count_nonzero(got[impl].first_exercise != want["first_ex"])
+            assert mism == 0 or want["min_gap"] < 1e-9 * K, (impl, mism)
+        assert np.array_equal(got["3"].first_exercise, got["0"].first_exercise)
+        assert np.max(np.abs(got["3"].v0 - got["0"].v0)) <= 1e-9 * K
+        assert abs(got["3"].price - got["0"].price) <= 1e-12 * want["price"]
+    ps.close()
