@@ -762,55 +762,67 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma64_kernel(SweepArgs a,
         const int64_t i0 = tile_of(it) * TMA_TILE, ia = i0 + 4 * tid, ib = ia + 2048;
         const float sv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
         const float pv[8] = {pA.x, pA.y, pA.z, pA.w, pB.x, pB.y, pB.z, pB.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int64_t i = (e < 4 ? ia : ib) + (e & 3);
-            const bool live = i < a.n;
-            const double s = f2d(sv[e]);
-            const double pay = payoff_fn(a.is_call, s, a.K);
-            if (mode == 2) {
-                v[e] = pay;  // LSMPricer.cpp:37-40
-            } else if (mode == 1) {
-                v[e] = v[e] * a.disc;  // LSMPricer.cpp:43-49
-            } else {
-                const double x = (s - mu) * inv_s;
-                double cont = c[P];
-#pragma unroll
-                for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
-                const bool itm = pay > 1e-14;   // LSMPricer.cpp:55
-                const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate (LSMPricer.cpp:85)
-                const double carried = pay < 1e-14 ? v[e] * a.disc : 0.0;  // LSMPricer.cpp:89-94; == 1e-14 keeps the initial 0 (:35)
-                v[e] = itm ? (ex ? pay : cont) : carried;
-                if (a.tau && itm && ex && live) a.tau[i] = a.j;
-            }
-            if (!live) v[e] = 0.0;  // pad lanes: never NaN / Inf in the carry
-        }
-        if (ia < a.ld) { stg2d_stream(V + ia, v[0], v[1]); stg2d_stream(V + ia + 2, v[2], v[3]); }
-        if (ib < a.ld) { stg2d_stream(V + ib, v[4], v[5]); stg2d_stream(V + ib + 2, v[6], v[7]); }
-        if (a.do_moments) {
+        // The ALU pipe (selects, 64-bit integer compares, software float->double widening) was what bound the first version of
+        // this kernel (ncu profiles/r02d: 133 instructions per path, ALU 68%, issue 70%, DRAM 73% of the copy peak), not the
+        // fp64 pipe (33 operations per path): whole tiles therefore run without any bounds arithmetic, the widening is the
+        // hardware conversion, and the in-the-money filter of the moments is a 0/1 multiplier on the fp64 pipe.
+        auto body = [&](auto tail_tag) {
+            constexpr bool TAILT = decltype(tail_tag)::value;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int64_t i = (e < 4 ? ia : ib) + (e & 3);
-                const double sp = f2d(pv[e]);
-                if (i < a.n && payoff_fn(a.is_call, sp, a.K) > 1e-14) {  // LSMPricer.cpp:51-58 for step j-1
-                    const double x = (sp - mu_p) * inv_s_p, y = v[e] * a.disc;  // LSMPricer.cpp:69
-                    double xp = x;
-                    ++cnt;
-                    acc[2 * P + 1] += y;
+                const bool live = !TAILT || ((e < 4 ? ia : ib) + (e & 3) < a.n);
+                const double s = (double)sv[e];
+                const double pay = payoff_fn(a.is_call, s, a.K);
+                if (mode == 2) {
+                    v[e] = pay;  // LSMPricer.cpp:37-40
+                } else if (mode == 1) {
+                    v[e] = v[e] * a.disc;  // LSMPricer.cpp:43-49
+                } else {
+                    const double x = (s - mu) * inv_s;
+                    double cont = c[P];
 #pragma unroll
-                    for (int k = 1; k <= 2 * P; ++k) {
-                        acc[k] += xp;
-                        if (k <= P) acc[2 * P + 1 + k] = fma(xp, y, acc[2 * P + 1 + k]);
-                        if (k < 2 * P) xp *= x;
-                    }
+                    for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, c[k]);
+                    const bool itm = pay > 1e-14;   // LSMPricer.cpp:55
+                    const bool ex = !(pay < cont);  // std::max(immediate, cont) returns immediate (LSMPricer.cpp:85)
+                    const double carried = pay < 1e-14 ? v[e] * a.disc : 0.0;  // LSMPricer.cpp:89-94; == 1e-14 keeps the initial 0 (:35)
+                    v[e] = itm ? (ex ? pay : cont) : carried;
+                    if (a.tau && itm && ex && live) a.tau[(e < 4 ? ia : ib) + (e & 3)] = a.j;
+                }
+                if (TAILT && !live) v[e] = 0.0;  // pad lanes: never NaN / Inf in the carry
+            }
+            if (!TAILT || ia < a.ld) { stg2d_stream(V + ia, v[0], v[1]); stg2d_stream(V + ia + 2, v[2], v[3]); }
+            if (!TAILT || ib < a.ld) { stg2d_stream(V + ib, v[4], v[5]); stg2d_stream(V + ib + 2, v[6], v[7]); }
+            if (a.do_moments) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool live = !TAILT || ((e < 4 ? ia : ib) + (e & 3) < a.n);
+                    const double sp = live ? (double)pv[e] : 0.0;
+                    const bool in = live && payoff_fn(a.is_call, sp, a.K) > 1e-14;  // LSMPricer.cpp:51-58 for step j-1
+                    const double msk = in ? 1.0 : 0.0;
+                    const double x = ((sp - mu_p) * inv_s_p) * msk, y = (v[e] * a.disc) * msk;  // LSMPricer.cpp:69; 0 kills every moment
+                    cnt += in ? 1 : 0;
+                    // power sums as FMA products: x^k = x^ceil(k/2) * x^floor(k/2) goes straight into the accumulating DFMA
+                    double xp[P + 1];
+                    xp[0] = x;
+                    if (P >= 1) xp[1] = x;
+#pragma unroll
+                    for (int k = 2; k <= P; ++k) xp[k] = xp[k - 1] * x;
+                    acc[2 * P + 1] += y;
+                    if (P >= 1) acc[1] += x;
+#pragma unroll
+                    for (int k = 2; k <= 2 * P; ++k) acc[k] = fma(xp[(k + 1) / 2], xp[k / 2], acc[k]);
+#pragma unroll
+                    for (int k = 1; k <= P; ++k) acc[2 * P + 1 + k] = fma(xp[k], y, acc[2 * P + 1 + k]);
                 }
             }
-        }
-        if (a.do_final) {
+            if (a.do_final) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if ((e < 4 ? ia : ib) + (e & 3) < a.n) acc[0] += v[e];
-        }
+                for (int e = 0; e < 8; ++e)
+                    if (!TAILT || (e < 4 ? ia : ib) + (e & 3) < a.n) acc[0] += v[e];
+            }
+        };
+        if (i0 + TMA_TILE <= a.n) body(std::false_type{});
+        else body(std::true_type{});
     }
     if (a.do_moments) acc[0] = (double)cnt;
     if (a.do_moments || a.do_final) sweep_epilogue<NV, P, TMA_NT>(a, acc);

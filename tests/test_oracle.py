@@ -266,3 +266,19 @@ def test_product_estimators_on_the_host_match_the_oracle(port):
             assert (np.isnan(a[k]) and np.isnan(b[k])) or a[k] == pytest.approx(b[k], rel=1e-11, abs=1e-300), (n, k)
     with pytest.raises(m.McpError, match="Historical prices vector too small."):
         m.Engine.estimate_rbergomi_params([100.0])
+
+
+def test_numpy_philox_restatement_matches_the_port_and_the_known_answers(port):
+    """tests/philox_np.py (used by the GPU known-answer test on a million counters) is itself pinned here."""
+    from philox_np import philox4x32_10
+    kats = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+            ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kats:
+        assert [int(x) for x in philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]] == want
+    rng = np.random.default_rng(3)
+    ctr = rng.integers(0, 2**32, size=(200, 4), dtype=np.uint64).astype(np.uint32)
+    key = [0x9abcdef0, 0x12345678]
+    got = philox4x32_10(ctr, key)
+    for i in range(200):
+        assert list(port.philox(ctr[i], key)) == [int(x) for x in got[i]]
