@@ -63,7 +63,7 @@ enum mcp_basis { MCP_BASIS_MONOMIAL = 0,           /* 1, S, S^2 ... (LSMPricer.c
 /* ------------------------------------------------------------------------------------------- engine */
 int mcp_abi_version(void);
 int mcp_create(int device, mcp_ctx **out);
-int mcp_destroy(mcp_ctx *ctx);
+int mcp_destroy(mcp_ctx *ctx); /* also releases every pathset of this ctx that is still alive: their handles die with it */
 const char *mcp_last_error(const mcp_ctx *ctx); /* ctx may be NULL: error of the last failed mcp_create */
 int mcp_set_stream(mcp_ctx *ctx, void *cuda_stream); /* run on a caller-owned cudaStream_t (NULL = own stream) */
 int mcp_synchronize(mcp_ctx *ctx);
@@ -219,7 +219,9 @@ int mcp_price_surface_rbergomi_lsm(mcp_ctx *ctx, const mcp_rbergomi_params *mode
  * reference uses 250, :719) rough-vol paths of row.n_steps steps (<= 512) are generated and priced by all four
  * pricers with the reference's per-row settings (exercise dates 0 .. n_steps-1, :780-783).  Three kernel launches per
  * batch instead of several per row and pricer.  Paths of row k are keyed by (seed, path_offset + k * n_paths + i), i.e.
- * the paths mcp_gen_rbergomi(.., seed, path_offset + k * n_paths) generates. */
+ * the paths mcp_gen_rbergomi(.., seed, path_offset + k * n_paths) generates.  A row whose model is degenerate (H < 0 -- the
+ * reference's DFA slope is unclamped --, |rho| > 1, xi < 0, dt <= 0, NaN) gets NaN in all five outputs, which is what the
+ * reference's NaN paths lead to for that row (PredictionGen.cpp:753-777); the rest of the batch is priced normally. */
 typedef struct mcp_row {
     mcp_rbergomi_params model; /* from mcp_estimate_rbergomi_params(history) or explicit */
     int n_steps;               /* floor(maturity * 252) in the reference (:718); rows with n_steps < 1 yield zeros (:720-733) */

@@ -89,6 +89,8 @@ struct mcp_ctx {
     size_t slab_pool_bytes = 0;
     // cached pathset for mcp_price_rbergomi_lsm
     mcp_pathset* cached_ps = nullptr;
+    // every pathset created on this ctx and not destroyed yet: mcp_destroy releases what the caller forgot
+    std::vector<mcp_pathset*> live_ps;
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;  // grow-only pool

@@ -234,6 +234,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->cached_ps) mcp_pathset_destroy(ctx->cached_ps);
+    while (!ctx->live_ps.empty()) mcp_pathset_destroy(ctx->live_ps.back());  // handles the caller never destroyed (they are dead after this)
     for (auto& blk : ctx->slab_pool) cudaFree(blk.first);
     ctx->slab_pool.clear();
     xchg_teardown(ctx);
@@ -244,7 +245,8 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (ctx->carry) cudaFree(ctx->carry);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stage) cudaFreeHost(ctx->stage);
-    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->prof_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -344,10 +346,11 @@ int mcp_comm_info(const mcp_ctx* ctx, int* rank, int* nranks) {
 }  // extern "C"
 
 cudaEvent_t mcp_prof_event(mcp_ctx* ctx, size_t i) {
-    while (ctx->prof_ev.size() <= i) {
+    if (ctx->prof_ev.size() <= i) ctx->prof_ev.resize(i + 1, nullptr);  // slots are created on first use
+    if (!ctx->prof_ev[i]) {
         cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        ctx->prof_ev.push_back(e);
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->prof_ev[i] = e;
     }
     return ctx->prof_ev[i];
 }

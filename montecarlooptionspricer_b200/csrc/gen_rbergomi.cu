@@ -758,8 +758,10 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
         const int n = n_steps[r];
         if (n < 1) { R.P.n_paths = 0; R.P.Mp = 1; continue; }  // no tiles: the kernel's tile loop is empty
         if (n > 512) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: n_steps %d > 512", n);
-        if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0))
-            return mcp_fail(ctx, MCP_ERR_DOMAIN, "rows: row %d needs dt > 0, H >= 0, |rho| <= 1, xi >= 0", r);
+        // A degenerate model (the reference's unclamped DFA slope does go negative on real histories, RoughVolatility.cpp:120-149)
+        // makes the reference write NaN paths for THAT row only (PredictionGen.cpp:753-777 rejects the row and goes on): such a
+        // row gets no tiles here and the caller (mcp_price_rows) reports NaN for it; the other rows of the batch are priced.
+        if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0)) { R.P.n_paths = 0; R.P.Mp = 1; continue; }
         const int Mp = next_pow2(n);
         R.P.Mp = Mp;
         R.table_off = (int64_t)tables_bytes;
@@ -776,6 +778,7 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
             const int n = n_steps[r];
             if (n < 1) continue;
             const mcp_rbergomi_params* prm = (const mcp_rbergomi_params*)((const unsigned char*)models + (size_t)r * model_stride_bytes);
+            if (!(prm->dt > 0.0) || !(prm->H >= 0.0) || !(fabs(prm->rho) <= 1.0) || !(prm->xi >= 0.0)) continue;  // degenerate: no tiles (pass 1)
             RbRow& R = rows[(size_t)r];
             mcp_rbergomi_tables(n, prm->H, prm->eta, prm->dt, prm->xi, phis, tw, comp2, pos, &R.P.Mp, &R.P.lgMp, &R.P.lg_radix, &R.P.n_stage);
             const int Mp = R.P.Mp;

@@ -1802,9 +1802,9 @@ extern "C" int mcp_price_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_params* m
         MCP_TRY(mcp_pathset_create(ctx, n_paths, n_steps, MCP_F32, &ps));
         ctx->cached_ps = ps;
     }
-    cudaEvent_t g0, g1;
-    MCP_CUDA(ctx, cudaEventCreate(&g0));
-    MCP_CUDA(ctx, cudaEventCreate(&g1));
+    // events from the ctx pool (created once, slots far above the per-step profiling events): no create / destroy per call
+    cudaEvent_t g0 = mcp_prof_event(ctx, 4094), g1 = mcp_prof_event(ctx, 4095);
+    if (!g0 || !g1) return mcp_fail(ctx, MCP_ERR_CUDA, "cudaEventCreate failed");
     MCP_CUDA(ctx, cudaEventRecord(g0, ctx->stream));
     int rc = mcp_gen_rbergomi(ctx, ps, model, seed, path_offset, nullptr, nullptr);
     if (rc == MCP_OK) {
@@ -1812,7 +1812,5 @@ extern "C" int mcp_price_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_params* m
         rc = mcp_lsm_price(ctx, ps, lsm, res, nullptr, nullptr, nullptr);
         if (rc == MCP_OK && gen_ms) cudaEventElapsedTime(gen_ms, g0, g1);
     }
-    cudaEventDestroy(g0);
-    cudaEventDestroy(g1);
     return rc;
 }

@@ -54,6 +54,7 @@ int mcp_pathset_create(mcp_ctx* ctx, int64_t n_paths, int n_steps, int dtype, mc
             return mcp_fail(ctx, MCP_ERR_CUDA, "pathset: clearing the pad columns failed: %s", cudaGetErrorString(e));
         }
     }
+    ctx->live_ps.push_back(ps);
     *out = ps;
     return MCP_OK;
 }
@@ -62,6 +63,8 @@ int mcp_pathset_destroy(mcp_pathset* ps) {
     if (!ps) return MCP_OK;
     cudaSetDevice(ps->ctx->device);
     mcp_ctx* ctx = ps->ctx;
+    for (size_t i = 0; i < ctx->live_ps.size(); ++i)
+        if (ctx->live_ps[i] == ps) { ctx->live_ps.erase(ctx->live_ps.begin() + (long)i); break; }
     if (ps->capacity > ((size_t)256 << 20)) cudaStreamSynchronize(ctx->stream);  // pooled blocks are reused in stream order instead
     if (ctx->cached_ps == ps) ctx->cached_ps = nullptr;
     constexpr size_t POOL_BLOCK_MAX = (size_t)256 << 20, POOL_TOTAL_MAX = (size_t)1 << 30;

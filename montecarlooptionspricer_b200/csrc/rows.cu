@@ -94,8 +94,8 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
     int max_steps = 1;
     for (int r = 0; r < n_rows; ++r) {
         if (rows[r].n_steps > 512) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: row %d has %d steps (> 512)", r, rows[r].n_steps);
-        if (rows[r].n_steps >= 1 && !(rows[r].sigma > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "AsymptoticAnalysis: Volatility must be positive.");
-        if (rows[r].n_steps >= 1 && !(rows[r].strike > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "BranchingProcesses: Strike must be positive.");
+        if (rows[r].n_steps >= 1 && !(rows[r].sigma > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "AsymptoticAnalysis: Volatility must be positive. (row %d)", r);
+        if (rows[r].n_steps >= 1 && !(rows[r].strike > 0.0)) return mcp_fail(ctx, MCP_ERR_DOMAIN, "BranchingProcesses: Strike must be positive. (row %d)", r);
         if (rows[r].n_steps > max_steps) max_steps = rows[r].n_steps;
     }
     const int64_t ld = mcp_round_up(n_paths, 128);
@@ -128,11 +128,13 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
             const mcp_row& R = rows[r0 + k];
             RowDev& D = h_rows[(size_t)k];
             D.slab_off = (int64_t)k * slab_stride;
-            D.n_steps = R.n_steps;
+            // a degenerate model (H < 0, |rho| > 1, xi < 0, NaN ...) spoils only its own row: no paths, NaN results (see mcp_rows_generate)
+            const bool degenerate = !(R.model.dt > 0.0) || !(R.model.H >= 0.0) || !(fabs(R.model.rho) <= 1.0) || !(R.model.xi >= 0.0);
+            D.n_steps = degenerate ? 0 : R.n_steps;
             D.is_call = R.is_call;
             D.K = R.strike; D.r = R.r; D.dt = R.dt; D.maturity = R.maturity; D.sigma = R.sigma; D.dividend = R.dividend;
             D.disc = exp(-R.r * R.dt);
-            steps[(size_t)k] = R.n_steps;
+            steps[(size_t)k] = D.n_steps;
         }
         cudaEventRecord(e0, ctx->stream);
         rc = mcp_rows_generate(ctx, &rows[r0].model, sizeof(mcp_row), steps.data(), nr, n_paths, seed, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_slabs,
@@ -155,6 +157,10 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
             o.lsm = h_out[(size_t)k * 8 + 2];
             o.martingale = h_out[(size_t)k * 8 + 3];
             o.lsm_std_error = h_out[(size_t)k * 8 + 4];
+            if (h_rows[(size_t)k].n_steps != rows[r0 + k].n_steps) {  // degenerate model: what the reference's NaN paths give
+                const double qnan = nan("");
+                o.asymptotic = o.branching = o.lsm = o.martingale = o.lsm_std_error = qnan;
+            }
         }
         float a = 0.f, b = 0.f;
         if (cudaEventElapsedTime(&a, e0, e1) == cudaSuccess) g_total += a;

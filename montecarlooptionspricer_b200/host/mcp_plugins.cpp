@@ -36,8 +36,9 @@ Engine& pick(Engine* e) { return e ? *e : Engine::thread_default(); }
 // ------------------------------------------------------------------------------------------- upload cache
 // The reference's row loop hands the SAME path matrix to four pricers in a row (PredictionGen.cpp:788-791).  Each
 // Engine therefore keeps the last uploaded matrix on the device, keyed by its dimensions and a 64-bit hash of its
-// contents: the second to fourth pricer of a row find their slab already resident.  Matrices above 64 MiB are not
-// cached (hashing them would cost as much as the copy).
+// contents: the second to fourth pricer of a row find their slab already resident.  A hash match is only a candidate:
+// the hit is confirmed against a host copy of the cached matrix (memcmp, row by row), so a collision can never price
+// the previous matrix.  Matrices above 64 MiB are not cached (hashing them would cost as much as the copy).
 namespace {
 
 uint64_t hash_rows(const PathMatrix& paths) {
@@ -106,10 +107,14 @@ DevicePaths::DevicePaths(Engine& eng, const PathMatrix& paths, int dtype) {
     uint64_t h = 0;
     if (cacheable) {
         h = hash_rows(paths);
-        if (eng.cache_ps_ && eng.cache_n_ == n && eng.cache_m_ == m && eng.cache_hash_ == h) {
-            ps_ = eng.cache_ps_;  // resident already
-            owned_ = false;
-            return;
+        if (eng.cache_ps_ && eng.cache_n_ == n && eng.cache_m_ == m && eng.cache_hash_ == h && eng.cache_copy_.size() == n * m) {
+            bool same = true;
+            for (size_t i = 0; i < n && same; ++i) same = std::memcmp(eng.cache_copy_.data() + i * m, rows[i], m * sizeof(double)) == 0;
+            if (same) {
+                ps_ = eng.cache_ps_;  // resident already
+                owned_ = false;
+                return;
+            }
         }
     }
     eng.check(mcp_pathset_create(eng.handle(), (int64_t)n, (int)m - 1, dtype, &ps_));
@@ -122,6 +127,8 @@ DevicePaths::DevicePaths(Engine& eng, const PathMatrix& paths, int dtype) {
     if (cacheable) {
         if (eng.cache_ps_) mcp_pathset_destroy(eng.cache_ps_);
         eng.cache_ps_ = ps_; eng.cache_n_ = n; eng.cache_m_ = m; eng.cache_hash_ = h;
+        eng.cache_copy_.resize(n * m);
+        for (size_t i = 0; i < n; ++i) std::memcpy(eng.cache_copy_.data() + i * m, rows[i], m * sizeof(double));
         owned_ = false;  // the engine's cache owns it now
     }
 }

@@ -52,6 +52,7 @@ private:
     mcp_pathset* cache_ps_ = nullptr;
     size_t cache_n_ = 0, cache_m_ = 0;
     uint64_t cache_hash_ = 0;
+    std::vector<double> cache_copy_;  // host copy of the cached matrix: a hash match is CONFIRMED by comparing contents
 };
 
 // Device-resident copy of a caller's path matrix (fp64 slab, time-major).  Matrices up to 64 MiB are kept in the

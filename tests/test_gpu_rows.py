@@ -71,3 +71,22 @@ def test_batched_rows_many_rows_and_error_contract(engine):
         engine.price_rows([bad])
     with pytest.raises(m.McpError, match="n_paths"):
         engine.price_rows(rows[:2], n_paths=5000)
+
+
+def test_a_degenerate_row_spoils_only_itself(engine):
+    """The reference's unclamped DFA slope can go negative on real histories (RoughVolatility.cpp:120-149): it then writes NaN
+    paths for THAT row and PredictionGen rejects the row (:753-777).  The batched driver must not abort the batch."""
+    rng = np.random.default_rng(5)
+    rows = make_rows(rng, 12)
+    good, _, _ = engine.price_rows(rows, n_paths=250, seed=3)
+    bad = [dict(r, model=dict(r["model"])) for r in rows]
+    live = [k for k, r in enumerate(rows) if r["n_steps"] >= 1]
+    k_h, k_rho = live[0], live[1]
+    bad[k_h]["model"]["H"] = -0.07
+    bad[k_rho]["model"]["rho"] = float("nan")
+    out, _, _ = engine.price_rows(bad, n_paths=250, seed=3)
+    for k in range(len(rows)):
+        if k in (k_h, k_rho):
+            assert np.all(np.isnan(out[k]))
+        else:
+            assert np.array_equal(out[k], good[k])  # paths are keyed by (seed, row, path): untouched by the neighbours
