@@ -127,11 +127,12 @@ def lib() -> C.CDLL:
     """Load libmcp_b200.so (built by montecarlooptionspricer_b200.build).  There is no fallback."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("MCP_B200_LIB") or LIB_PATH   # MCP_B200_LIB: load another build of the SAME library (libmcp_b200_dbg.so)
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                f"{path} is missing: the CUDA extension has not been built "
                 "(run `python -m montecarlooptionspricer_b200.build`). This package has no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res

@@ -18,6 +18,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "libmcp_b200.so")
+LIB_DBG = os.path.join(PKG, "libmcp_b200_dbg.so")   # same library with MCP_DEBUG_BOUNDS index checks in the sweep kernels
 PLUGINS = os.path.join(PKG, "libmcp_b200_plugins.so")
 DEMO = os.path.join(HOST, "plugin_rows_demo")
 LATENCY = os.path.join(HOST, "plugin_latency")
@@ -71,6 +72,28 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_debug(force: bool = False) -> str:
+    """libmcp_b200_dbg.so: lsm.cu recompiled with -DMCP_DEBUG_BOUNDS=1 (index checks + ring canaries in the asynchronous sweep
+    kernels, see csrc/lsm.cu), linked with the release objects of the other translation units.  Loaded by
+    tests/test_gpu_debug_bounds.py through MCP_B200_LIB; compute-sanitizer is closed on the development pool."""
+    build_cuda(force=False)
+    objdir, dbgdir = os.path.join(PKG, "build"), os.path.join(PKG, "build", "dbg")
+    os.makedirs(dbgdir, exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    src = os.path.join(CSRC, "lsm.cu")
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "mcp_b200.h")]
+    obj = os.path.join(dbgdir, "lsm.o")
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    if force or not _newer(obj, [src] + hdrs):
+        subprocess.run([_nvcc()] + flags + ["-DMCP_DEBUG_BOUNDS=1", "-c", src, "-o", obj], check=True, env=env, cwd=CSRC)
+    objs = [obj] + [os.path.join(objdir, s[:-3] + ".o") for s in CU_SOURCES if s != "lsm.cu"]
+    if force or not _newer(LIB_DBG, objs):
+        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_DBG, "-ldl"], check=True, env=env)
+    return LIB_DBG
+
+
 def build_plugins(force: bool = False) -> str:
     """C++ host plugin classes (reference signatures) over the C ABI + the PredictionGen-shaped demo caller."""
     src = os.path.join(HOST, "mcp_plugins.cpp")
@@ -94,11 +117,13 @@ def build_plugins(force: bool = False) -> str:
     return PLUGINS
 
 
-def build_all(force: bool = False, verbose: bool = False) -> None:
+def build_all(force: bool = False, verbose: bool = False, debug: bool = True) -> None:
     build_cuda(force=force, verbose=verbose)
     build_plugins(force=force)
+    if debug:
+        build_debug(force=force)
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--no-debug" not in sys.argv)
     print(LIB)

@@ -45,6 +45,41 @@
 #include "lsm_solve.cuh"
 #include "small_bodies.cuh"
 
+// ---------------------------------------------------------------------------------------------------------
+// MCP_DEBUG_BOUNDS build (python -m montecarlooptionspricer_b200.build --debug -> libmcp_b200_dbg.so): compute-sanitizer is
+// closed on the development pool, so the asynchronous parts -- bulk-copy ring, cross-step cursors, exchange rows --
+// carry their own index checks.  Every check that fails bumps a counter (class below) instead of corrupting memory
+// silently; tests/test_gpu_debug_bounds.py runs ragged sizes through every sweep kernel and requires all counters zero.
+// In a normal build the macros vanish.
+// ---------------------------------------------------------------------------------------------------------
+enum McpDbgClass { DBG_CARRY_STORE = 0, DBG_TAU_STORE = 1, DBG_RING_ISSUE = 2, DBG_RING_STAGE = 3, DBG_RING_CANARY = 4, DBG_XCHG_ROW = 5, DBG_NCLASS = 8 };
+#ifdef MCP_DEBUG_BOUNDS
+__device__ unsigned int g_dbg_violations[DBG_NCLASS];
+#define MCP_DBG_CHECK(cond, cls)                                  \
+    do {                                                          \
+        if (!(cond)) atomicAdd(&g_dbg_violations[(cls)], 1u);     \
+    } while (0)
+constexpr int MCP_DBG_CANARY_BYTES = 128;  // between the last ring stage and the barriers
+constexpr unsigned int MCP_DBG_CANARY = 0xC0FFEE11u;
+#else
+#define MCP_DBG_CHECK(cond, cls) \
+    do {                         \
+    } while (0)
+constexpr int MCP_DBG_CANARY_BYTES = 0;
+#endif
+
+extern "C" int mcp_debug_violations(unsigned int* out, int n) {
+#ifdef MCP_DEBUG_BOUNDS
+    unsigned int v[DBG_NCLASS];
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(v, g_dbg_violations, sizeof(v)) != cudaSuccess) return -2;
+    for (int i = 0; i < n && i < DBG_NCLASS; ++i) out[i] = v[i];
+    return DBG_NCLASS;
+#else
+    (void)out; (void)n;
+    return 0;  // not a debug build
+#endif
+}
+
 namespace {
 
 constexpr int LSM_NT = 256;
@@ -374,6 +409,8 @@ __device__ __forceinline__ void fast2_compute(const SweepArgs& a, const StepK& g
                 v[q].y = pay.y > 1e-14f ? fmaxf(pay.y, cont.y) : vd.y;
                 if (TAU) {
                     const int64_t ib = (q < 2 ? idx0 : idx1) + 2 * (q & 1);
+                    MCP_DBG_CHECK(!ok[2 * q] || (ib >= 0 && ib < a.n), DBG_TAU_STORE);
+                    MCP_DBG_CHECK(!ok[2 * q + 1] || (ib + 1 >= 0 && ib + 1 < a.n), DBG_TAU_STORE);
                     if (pay.x > 1e-14f && !(pay.x < cont.x) && ok[2 * q]) a.tau[ib] = a.j;
                     if (pay.y > 1e-14f && !(pay.y < cont.y) && ok[2 * q + 1]) a.tau[ib + 1] = a.j;
                 }
@@ -547,9 +584,13 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     constexpr int FLUSH = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES);  // "stage filled" barriers (TMA completes them)
-    uint64_t* empty = full + 8;                                                                       // "stage consumed" barriers (one arrival per warp)
-    double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * TMA_STAGE_BYTES + 128);  // [NV][TMA_NT]
+    unsigned char* after_ring = smem_raw + (size_t)n_stages * TMA_STAGE_BYTES + MCP_DBG_CANARY_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(after_ring);  // "stage filled" barriers (TMA completes them)
+    uint64_t* empty = full + 8;                                // "stage consumed" barriers (one arrival per warp)
+    double* sacc = reinterpret_cast<double*>(after_ring + 128);  // [NV][TMA_NT]
+#ifdef MCP_DEBUG_BOUNDS
+    if (threadIdx.x < MCP_DBG_CANARY_BYTES / 4) reinterpret_cast<unsigned int*>(after_ring - MCP_DBG_CANARY_BYTES)[threadIdx.x] = MCP_DBG_CANARY;
+#endif
     const float* __restrict__ Sj = reinterpret_cast<const float*>(a.S) + (int64_t)a.j * a.ld;
     const float* __restrict__ Sp = reinterpret_cast<const float*>(a.S) + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
     float* __restrict__ V = reinterpret_cast<float*>(a.V);
@@ -578,6 +619,8 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
         const int64_t cnt = a.ld - i0 < TMA_TILE ? a.ld - i0 : TMA_TILE;  // rows are padded to ld (multiple of 128)
         const uint32_t bytes = (uint32_t)cnt * 4u;
         float* dst = ring + (size_t)st * (3 * TMA_TILE);
+        MCP_DBG_CHECK(st >= 0 && st < n_stages && it >= 0 && it < my_tiles, DBG_RING_STAGE);
+        MCP_DBG_CHECK(i0 >= 0 && cnt > 0 && cnt <= TMA_TILE && i0 + cnt <= a.ld && (bytes & 15u) == 0u, DBG_RING_ISSUE);
         if (part_s) {
             mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (want_v ? 1u : 0u)));
             bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
@@ -638,6 +681,7 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
         const bool whole = i0 + TMA_TILE <= a.n;
         if (whole) fast2_compute<P, TAU, false, KIND>(a, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
         else fast2_compute<P, TAU, true, KIND>(a, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+        MCP_DBG_CHECK(ia >= 0 && (!(whole || ia < a.ld) || ia + 4 <= a.ld) && (!(whole || ib < a.ld) || ib + 4 <= a.ld), DBG_CARRY_STORE);
         if (a.l2_resident) {
             if (whole || ia < a.ld) stg4_keep(V + ia, v8.q[0], v8.q[1]);
             if (whole || ib < a.ld) stg4_keep(V + ib, v8.q[2], v8.q[3]);
@@ -657,6 +701,9 @@ __global__ void __launch_bounds__(TMA_NT, 1) lsm_sweep_tma_kernel(SweepArgs a, i
     };
     if (mode == 0 && a.do_moments && !a.do_final) run_tiles(std::integral_constant<int, 0>{});
     else run_tiles(std::integral_constant<int, 1>{});
+#ifdef MCP_DEBUG_BOUNDS
+    if (tid < MCP_DBG_CANARY_BYTES / 4) MCP_DBG_CHECK(reinterpret_cast<unsigned int*>(after_ring - MCP_DBG_CANARY_BYTES)[tid] == MCP_DBG_CANARY, DBG_RING_CANARY);
+#endif
     if (a.do_moments || a.do_final) {
         double acc[NV];
 #pragma unroll
@@ -917,6 +964,8 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
         const int64_t cnt = a.ld - i0 < MULTI_TILE ? a.ld - i0 : MULTI_TILE;
         const uint32_t bytes = (uint32_t)cnt * 4u;
         float* dst = ring + (size_t)st * MULTI_STAGE_FLOATS;
+        MCP_DBG_CHECK(st >= 0 && st < n_stages && it >= 0 && it < my_tiles, DBG_RING_STAGE);
+        MCP_DBG_CHECK(i0 >= 0 && cnt > 0 && cnt <= MULTI_TILE && i0 + cnt <= a.ld && (bytes & 15u) == 0u && a.C >= 1 && a.C <= MULTI_MAXC, DBG_RING_ISSUE);
         mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (mode != 2 ? (uint32_t)a.C : 0u)));
         bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
         if (a.do_moments) bulk_g2s(dst + MULTI_TILE, Sp + i0, bytes, full + st);
@@ -961,6 +1010,7 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
                 }
                 if (i0 + MULTI_TILE <= a.n) fast2_compute<P, false, false>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
                 else fast2_compute<P, false, true>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+                MCP_DBG_CHECK(ia >= 0 && (ia >= a.ld || ia + 4 <= a.ld) && (ib >= a.ld || ib + 4 <= a.ld), DBG_CARRY_STORE);
                 if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
                 if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
                 if (++since == FLUSH) {
@@ -1067,6 +1117,7 @@ __device__ __forceinline__ void xchg_allreduce(const McpXchg& x, unsigned long l
     const int tid = threadIdx.x, n = x.nranks;
     const size_t half = (size_t)(seq & 1ull) * (size_t)n;
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    MCP_DBG_CHECK(n >= 1 && n <= MCP_XMAX_RANKS && x.rank >= 0 && x.rank < n && 2 * NV <= MCP_XROW, DBG_XCHG_ROW);
     for (int idx = tid; idx < n * 2 * NV; idx += NT) {
         const int r = idx / (2 * NV), w = idx - r * (2 * NV);
         const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w >> 1]);
@@ -1392,7 +1443,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     }
     if (ps->dtype == MCP_F32 && carry == MCP_F32 && env_int("MCP_SWEEP_IMPL", 3) == 3 && ntile >= 2 * (int64_t)ctx->sm_count) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
-        const size_t fixed = 128 + (size_t)nv * TMA_NT * 8;
+        const size_t fixed = 128 + MCP_DBG_CANARY_BYTES + (size_t)nv * TMA_NT * 8;
         tma_stages = (int)((227u * 1024u - 12288u - fixed) / TMA_STAGE_BYTES);  // 12 KB: the kernel's static shared memory
         const int want = env_int("MCP_SWEEP_STAGES", 0);
         if (want > 0 && want < tma_stages) tma_stages = want;
@@ -1414,7 +1465,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     size_t px_smem = 0;
     if (!small && ps->dtype == MCP_F32 && carry == MCP_F32 && impl_env != 3 && (!multi_early || ctx->xchg.enabled)) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
-        const size_t fixed = 128 + (size_t)nv * px::NT * 8;
+        const size_t fixed = 128 + MCP_DBG_CANARY_BYTES + (size_t)nv * px::NT * 8;
         px_stages = (int)((227u * 1024u - 4096u - fixed) / px::STAGE_BYTES);
         const int want = env_int("MCP_SWEEP_STAGES", 0);
         if (want > 0 && want < px_stages) px_stages = want;

@@ -151,6 +151,7 @@ __device__ __forceinline__ bool exchange(const McpPx& x, unsigned long long seq,
     if (x.nranks <= 1) return my_status == 0;
     const unsigned long long tag = tag_of(seq);
     const int nwords = 2 * nv + 1;
+    MCP_DBG_CHECK(nwords <= MCP_PX_BIGW && x.nranks <= MCP_XMAX_RANKS && x.rank >= 0 && x.rank < x.nranks, DBG_XCHG_ROW);
     for (int i = threadIdx.x; i < x.nranks * nwords; i += NT) {
         const int r = i / nwords, k = i - r * nwords;
         unsigned long long payload;
@@ -180,6 +181,7 @@ static_assert(2 * (MAXP + 1) + 1 <= MCP_PX_BCW, "broadcast slot");
 __device__ __forceinline__ void broadcast(const McpPx& x, unsigned long long seq, int nw, const double* vals, int nv, int status) {
     const unsigned long long tag = tag_of(seq);
     const int nwords = 2 * nv + 1;
+    MCP_DBG_CHECK(nwords <= MCP_PX_BCW && nw >= 1 && nw <= MCP_PX_MAXW, DBG_XCHG_ROW);
     for (int i = threadIdx.x; i < nw * nwords; i += NT) {
         const int w = i / nwords, k = i - w * nwords;
         unsigned long long payload = (unsigned long long)(unsigned int)status;
@@ -321,9 +323,13 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     constexpr int FLUSH = 8;
     const int n_stages = a.n_stages;
     float* ring = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * STAGE_BYTES);
+    unsigned char* after_ring = smem_raw + (size_t)n_stages * STAGE_BYTES + MCP_DBG_CANARY_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(after_ring);
     uint64_t* empty = full + 8;
-    double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * STAGE_BYTES + 128);  // [NV][NT]
+    double* sacc = reinterpret_cast<double*>(after_ring + 128);  // [NV][NT]
+#ifdef MCP_DEBUG_BOUNDS
+    if (threadIdx.x < MCP_DBG_CANARY_BYTES / 4) reinterpret_cast<unsigned int*>(after_ring - MCP_DBG_CANARY_BYTES)[threadIdx.x] = MCP_DBG_CANARY;
+#endif
     __shared__ double red[NT / 32][NV];
     __shared__ double s_c[COEF_LD + 4];  // c_0..c_P, then mu_j, 1/s_j, mu_{j-1}, 1/s_{j-1}
     __shared__ int s_stop;
@@ -365,12 +371,15 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
         const int64_t i0 = ((int64_t)w + cs.it * nw) * TILE;
         const uint32_t bytes = tile_bytes(i0);
         float* dst = ring + (size_t)cs.st * STAGE_FLOATS;
+        MCP_DBG_CHECK(cs.st >= 0 && cs.st < n_stages && cs.it >= 0 && cs.it < my_tiles && cs.s >= 0 && cs.s < M && cs.n < g_total, DBG_RING_STAGE);
+        MCP_DBG_CHECK(i0 >= 0 && bytes > 0 && bytes <= TILE * 4u && i0 + (int64_t)(bytes / 4u) <= a.ld && (bytes & 15u) == 0u && j >= 0 && j < M, DBG_RING_ISSUE);
         mbar_expect_tx(full + cs.st, bytes * (1u + (dm ? 1u : 0u) + (want_v ? 1u : 0u)));
         bulk_g2s_hint(dst, S + (int64_t)j * a.ld + i0, bytes, full + cs.st, pol_first);                      // last use of row j
         if (dm) bulk_g2s_hint(dst + TILE, S + (int64_t)(j - 1) * a.ld + i0, bytes, full + cs.st, pol_norm);  // read again next step
         advance(cs);
     };
     auto issue_carry = [&]() {
+        MCP_DBG_CHECK(cv.n < cs.n && cv.st >= 0 && cv.st < n_stages, DBG_RING_STAGE);  // the carry cursor never passes the slab cursor
         if (cv.s > 0) {
             const int64_t i0 = ((int64_t)w + cv.it * nw) * TILE;
             bulk_g2s_hint(ring + (size_t)cv.st * STAGE_FLOATS + 2 * TILE, V + i0, tile_bytes(i0), full + cv.st, a.l2_resident ? pol_norm : pol_first);
@@ -506,6 +515,8 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
             if (++cst == n_stages) { cst = 0; cpar ^= 1u; }
             const int64_t ia = i0 + 4 * tid, ib = ia + 2048;
             fast2_compute<P, TAU, TAILT, KIND>(sa, a.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+            MCP_DBG_CHECK(vp == V + ia && ia >= 0 && (!(!TAILT || ia < a.ld) || ia + 4 <= a.ld) && (!(!TAILT || ib < a.ld) || ib + 4 <= a.ld), DBG_CARRY_STORE);
+            MCP_DBG_CHECK(cst >= 0 && cst < n_stages, DBG_RING_STAGE);
             if (!TAILT || ia < a.ld) stg4_keep(vp, v8.q[0], v8.q[1]);
             if (!TAILT || ib < a.ld) stg4_keep(vp + 2048, v8.q[2], v8.q[3]);
             if (++since == FLUSH) {
@@ -541,6 +552,7 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
             since = 0;
             cnt = 0;
             __syncthreads();
+            MCP_DBG_CHECK(w >= 0 && w < MCP_PX_MAXW && 2 * NV <= MCP_PX_ROWW, DBG_XCHG_ROW);
             if (tid < NV) {
                 double t = 0.0;
 #pragma unroll
@@ -586,6 +598,9 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
             st_tagged_double(local_row(a.x, seq, w), 0, tt, tag_of(seq));
         }
     }
+#ifdef MCP_DEBUG_BOUNDS
+    if (tid < MCP_DBG_CANARY_BYTES / 4) MCP_DBG_CHECK(reinterpret_cast<unsigned int*>(after_ring - MCP_DBG_CANARY_BYTES)[tid] == MCP_DBG_CANARY, DBG_RING_CANARY);
+#endif
     // never leave with bulk copies in flight into this CTA's shared memory
     if (tid == 0) {
         while (cv.n < cs.n) issue_carry();  // (stop path) complete the armed barriers
