@@ -143,7 +143,10 @@ int mcp_philox_raw(mcp_ctx *ctx, uint64_t seed, uint64_t first, int64_t count, u
 typedef struct mcp_lsm_params {
     double r, strike, maturity, dt;
     int is_call;
-    int poly_order; /* 0..6 */
+    int poly_order; /* 0..6.  The reference accepts any order, but its raw-monomial design is rank deficient by Eigen's own rule from
+                     * order 5 on (S ~ 100): bdcSvd().solve() then drops directions (LSMPricer.cpp:76).  That cut is reproduced on the
+                     * device (csrc/lsm_solve.cuh: exercise indices and price match the reference for orders 5 and 6 as they do for
+                     * 1..4); orders above 6 would only add directions the reference discards and return MCP_ERR_UNSUPPORTED. */
     int basis;      /* mcp_basis: affects only the coefficient table that is returned */
     int carry;      /* mcp_dtype of the value carry V: MCP_F64 = parity mode, MCP_F32 = throughput mode */
 } mcp_lsm_params;

@@ -171,6 +171,7 @@ struct SweepArgs {
     unsigned long long seq;  // sequence number of this launch's exchange
     int l2_resident;    // two slab rows + the carry fit in L2: keep them there instead of streaming
     StepK g;            // contract constants of the packed-fp32 kernels (make_stepk)
+    int ref_rank;       // apply the reference's SVD rank cut in the solve (parity mode, and always for p >= 5; lsm_solve.cuh)
 };
 
 // Block-wide deterministic sum of NV doubles per thread -> row `blockIdx.x` of `partial`.
@@ -914,7 +915,7 @@ struct MultiArgs {
     unsigned int* counter;
     double K[MULTI_MAXC];
     double disc;
-    int C, M, is_call, j, terminal, do_moments, do_final;
+    int C, M, is_call, j, terminal, do_moments, do_final, ref_rank;
 };
 
 template <int P>
@@ -925,7 +926,8 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
     constexpr int NT = MULTI_MAXC * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES);  // "stage filled" (TMA completes them)
+    uint64_t* empty = full + 8;                                                                        // "stage consumed": one arrival per warp
     double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES + 128);  // [NV][NT]
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp = contract
     const bool active = c < a.C;
@@ -958,8 +960,7 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
         const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
         return (a.j & 1) ? (ntile - 1 - t) : t;
     };
-    auto issue = [&](int64_t it) {  // one elected thread: the two slab tiles and every contract's carry tile
-        const int st = (int)(it % n_stages);
+    auto issue = [&](int64_t it, int st) {  // one elected thread: the two slab tiles and every contract's carry tile
         const int64_t i0 = tile_of(it) * MULTI_TILE;
         const int64_t cnt = a.ld - i0 < MULTI_TILE ? a.ld - i0 : MULTI_TILE;
         const uint32_t bytes = (uint32_t)cnt * 4u;
@@ -973,16 +974,15 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
             for (int q = 0; q < a.C; ++q) bulk_g2s_hint(dst + (2 + q) * MULTI_TILE, a.V + (int64_t)q * a.ld + i0, bytes, full + st, pol);
     };
     if (tid == 0) {
-        for (int st = 0; st < n_stages; ++st) mbar_init(full + st, 1);
+        for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it);
+        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, (int)it);
     }
     __syncthreads();
 
-    int since = 0;
+    int since = 0, st = 0;
+    uint32_t parity = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
-        const int st = (int)(it % n_stages);
-        const uint32_t parity = (uint32_t)((it / n_stages) & 1);
         while (!mbar_try_wait(full + st, parity)) {}
         const float* buf = ring + (size_t)st * MULTI_STAGE_FLOATS;
         const float* vbuf = buf + (2 + cc) * MULTI_TILE;
@@ -1023,8 +1023,15 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
                 }
             }
         }
-        __syncthreads();  // every warp is done with the stage: refill it
-        if (tid == 0 && it + n_stages < my_tiles) issue(it + n_stages);
+        // this warp is done with the stage (it read the tiles straight from shared memory); once all 16 warps have said so the
+        // slot is refilled -- no block-wide barrier, warps drift apart by up to the ring depth
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+        if (tid == 0 && it + n_stages < my_tiles) {
+            while (!mbar_try_wait(empty + st, parity)) {}
+            issue(it + n_stages, st);
+        }
+        if (++st == n_stages) { st = 0; parity ^= 1u; }
     }
     if (!(a.do_moments || a.do_final)) return;
     // per-contract (per-warp) partial row of this CTA, in a fixed lane order
@@ -1055,7 +1062,10 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
         __syncwarp();
         if (lane == 0) {
             if (a.do_final) a.fin[c * 4] = tot[c][0];
-            else solve_normal_equations<P>(&tot[c][0], a.coef + ((int64_t)c * a.M + (a.j - 1)) * COEF_LD);
+            else {
+                const RefRank rr{a.mu[(int64_t)c * a.M + (a.j - 1)], a.inv_s[(int64_t)c * a.M + (a.j - 1)]};
+                solve_normal_equations<P>(&tot[c][0], a.coef + ((int64_t)c * a.M + (a.j - 1)) * COEF_LD, a.ref_rank ? &rr : nullptr);
+            }
         }
     }
     if (tid == 0) *a.counter = 0u;
@@ -1092,8 +1102,12 @@ __global__ void __launch_bounds__(256) lsm_reduce_kernel(const double* __restric
 }
 
 // Multi-GPU path: after the NCCL all-reduce of the moments every rank solves the same tiny system.
-__global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* __restrict__ coef_row) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) solve_dispatch(mom, p, coef_row);
+__global__ void lsm_solve_kernel(const double* __restrict__ mom, int p, double* __restrict__ coef_row, const double* __restrict__ mu,
+                                 const double* __restrict__ inv_s, int ref_rank) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const RefRank rr{*mu, *inv_s};
+        solve_dispatch(mom, p, coef_row, ref_rank ? &rr : nullptr);
+    }
 }
 
 // All-reduce (sum) of `vals[0..NV)` across GPUs through the peer-memory mailboxes, executed by ONE CTA per rank (the
@@ -1191,7 +1205,10 @@ __device__ __forceinline__ void sweep_epilogue(const SweepArgs& a, double (&acc)
     }
     if (threadIdx.x == 0) {
         *a.d.counter = 0u;
-        if (a.do_moments && a.solve_here) solve_normal_equations<P>(&red[0][0], a.d.coef + (int64_t)(a.j - 1) * COEF_LD);
+        if (a.do_moments && a.solve_here) {
+            const RefRank rr{a.d.mu[a.j - 1], a.d.inv_s[a.j - 1]};
+            solve_normal_equations<P>(&red[0][0], a.d.coef + (int64_t)(a.j - 1) * COEF_LD, a.ref_rank ? &rr : nullptr);
+        }
     }
 }
 
@@ -1465,7 +1482,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     size_t px_smem = 0;
     if (!small && ps->dtype == MCP_F32 && carry == MCP_F32 && impl_env != 3 && (!multi_early || ctx->xchg.enabled)) {
         const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
-        const size_t fixed = 128 + MCP_DBG_CANARY_BYTES + (size_t)nv * px::NT * 8;
+        const size_t fixed = 128 + MCP_DBG_CANARY_BYTES + (size_t)nv * (px::NT / 2) * 8;
         px_stages = (int)((227u * 1024u - 4096u - fixed) / px::STAGE_BYTES);
         const int want = env_int("MCP_SWEEP_STAGES", 0);
         if (want > 0 && want < px_stages) px_stages = want;
@@ -1473,6 +1490,8 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         int64_t w = ntile;  // a worker with more tiles than ring stages chains them across steps, one with fewer refills per step
         const int64_t wmax = (ctx->sm_count - 1 < MCP_PX_MAXW ? ctx->sm_count - 1 : MCP_PX_MAXW);
         if (w > wmax) w = wmax;
+        const int w_env = env_int("MCP_PX_WORKERS", 0);  // experiments: fewer streaming CTAs
+        if (w_env > 0 && w_env < w) w = w_env;
         if (w < 1) w = 1;
         const bool l2_fit = (size_t)N * 12 <= ((size_t)env_int("MCP_L2_RESIDENT_MB", 104) << 20);
         const bool want_px = (multi_early && ctx->xchg.enabled) || impl_env == 4 || (impl_env == 0 && l2_fit && ntile >= 32);
@@ -1538,6 +1557,9 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
     a.S = ps->data; a.ld = ps->ld; a.n = N; a.V = dV; a.tau = dTau; a.d = d;
     a.K = prm->strike; a.disc = disc; a.is_call = prm->is_call;
     a.g = make_stepk(prm->strike, disc, prm->is_call);
+    // the reference's SVD rank cut (lsm_solve.cuh): always in parity mode and for p >= 5, where it bites; the throughput mode skips
+    // the 3-sweep Jacobi of a full-rank 4 x 4 factor on its per-step critical path.  MCP_LSM_REF_RANK=0/1 overrides (tests).
+    a.ref_rank = env_int("MCP_LSM_REF_RANK", (carry == MCP_F64 || p >= 5) ? 1 : 0) ? 1 : 0;
     const bool multi = ctx->nranks > 1 && ctx->comm;
     const bool p2p = multi && ctx->xchg.enabled;
     if (p2p) a.x = ctx->xchg;
@@ -1558,7 +1580,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         memset(&pa, 0, sizeof(pa));
         pa.S = (const float*)ps->data; pa.ld = ps->ld; pa.n = N; pa.V = (float*)dV; pa.tau = dTau;
         pa.coef = d.coef; pa.mu = d.mu; pa.inv_s = d.inv_s; pa.ssum = d.ssum; pa.fin = d.fin; pa.kind = d.kind;
-        pa.K = prm->strike; pa.disc = disc; pa.is_call = prm->is_call; pa.M = M; pa.g = a.g;
+        pa.K = prm->strike; pa.disc = disc; pa.is_call = prm->is_call; pa.M = M; pa.g = a.g; pa.ref_rank = a.ref_rank;
         pa.ns = (int)(N < SAMPLE_MAX ? N : SAMPLE_MAX);
         pa.l2_resident = a.l2_resident; pa.n_workers = px_workers; pa.n_stages = px_stages;
         MCP_TRY(mcp_px_get(ctx, &pa.x));
@@ -1613,7 +1635,7 @@ extern "C" int mcp_lsm_price(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_
         if (ctx->profiling) cudaEventRecord(mcp_prof_event(ctx, 2 * (size_t)j + 1), st);
         if (a.do_moments && !a.solve_here) {  // multi-GPU: global moments, then every rank solves the same system
             MCP_TRY(mcp_allreduce_f64(ctx, d.moments, nm));
-            lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD);
+            lsm_solve_kernel<<<1, 32, 0, st>>>(d.moments, p, d.coef + (int64_t)(j - 1) * COEF_LD, d.mu + (j - 1), d.inv_s + (j - 1), a.ref_rank);
             MCP_LAUNCH_CHECK(ctx);
         }
     }
@@ -1762,7 +1784,7 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
     a.S = (const float*)ps->data; a.ld = ld; a.n = N; a.V = (float*)ctx->carry;
     a.coef = (double*)(sb + o_coef); a.mu = (double*)(sb + o_mu); a.inv_s = (double*)(sb + o_is);
     a.partial = (double*)(sb + o_part); a.fin = (double*)(sb + o_fin); a.kind = (int*)(sb + o_kind); a.counter = (unsigned int*)(sb + o_cnt);
-    a.disc = exp(-prm->r * prm->dt); a.M = M; a.is_call = prm->is_call;
+    a.disc = exp(-prm->r * prm->dt); a.M = M; a.is_call = prm->is_call; a.ref_rank = p >= 5 ? 1 : 0;
     double* d_ssum = (double*)(sb + o_ssum);
     std::vector<int> kind(M, STEP_NORMAL);
     for (int j = 0; j < M; ++j) kind[j] = ((double)j * prm->dt > prm->maturity) ? STEP_DISCOUNT : STEP_NORMAL;

@@ -51,7 +51,7 @@ struct Args {
     const int* kind;   // [M]
     double K, disc;
     StepK g;           // contract constants of the step arithmetic (host-made: they live in the constant bank)
-    int is_call, M, ns, l2_resident, n_workers, n_stages;
+    int is_call, M, ns, l2_resident, n_workers, n_stages, ref_rank;
     McpPx x;
     unsigned long long seq0;  // tag of this launch's first exchange; exchange e uses seq0 + e
     unsigned long long* trace;  // optional [M][n_workers + 1][4] globaltimer stamps (tools/px_trace.py); nullptr = off
@@ -86,10 +86,11 @@ __device__ __forceinline__ bool wait_word(const unsigned long long* p, unsigned 
     unsigned long long w = ld_word(p);
     if ((w & 0xffffffff00000000ull) != tag) {
         const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
         do {
             w = ld_word(p);
             if ((w & 0xffffffff00000000ull) == tag) break;
-            if (global_ns() - t0 > PX_TIMEOUT_NS) return false;
+            if ((++spins & 1023u) == 0u && global_ns() - t0 > PX_TIMEOUT_NS) return false;  // the timer is read once per 1024 polls
         } while (true);
     }
     *lo = (unsigned int)w;
@@ -121,6 +122,7 @@ __device__ __forceinline__ bool gather_rows(const unsigned long long* base, size
         for (int u = 0; u < U; ++u) all = all && ((w[u] & 0xffffffff00000000ull) == tag);
         if (!all) {
             const unsigned long long t0 = global_ns();
+            unsigned int spins = 0;
             while (true) {
                 all = true;
 #pragma unroll
@@ -129,7 +131,7 @@ __device__ __forceinline__ bool gather_rows(const unsigned long long* base, size
                     all = all && ((w[u] & 0xffffffff00000000ull) == tag);
                 }
                 if (all) break;
-                if (global_ns() - t0 > PX_TIMEOUT_NS || *(volatile int*)s_fail) { *(volatile int*)s_fail = 1; break; }
+                if ((++spins & 255u) == 0u && (global_ns() - t0 > PX_TIMEOUT_NS || *(volatile int*)s_fail)) { *(volatile int*)s_fail = 1; break; }
             }
         }
 #pragma unroll
@@ -282,7 +284,10 @@ __device__ void reducer(const Args& a, unsigned int* got /* shared, >= max(nw * 
             __syncthreads();
             broadcast(a.x, seq, nw, s_coef, 1, 0);
         } else {
-            if (tid == 0) solve_normal_equations<P>(vals, s_coef);
+            if (tid == 0) {
+                const RefRank rr{__ldcg(a.mu + j - 1), __ldcg(a.inv_s + j - 1)};
+                solve_normal_equations<P>(vals, s_coef, a.ref_rank ? &rr : nullptr);
+            }
             __syncthreads();
             if (tid < COEF_LD) a.coef[(size_t)(j - 1) * COEF_LD + tid] = s_coef[tid];
             broadcast(a.x, seq, nw, s_coef, P + 1, 0);
@@ -326,7 +331,8 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
     unsigned char* after_ring = smem_raw + (size_t)n_stages * STAGE_BYTES + MCP_DBG_CANARY_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(after_ring);
     uint64_t* empty = full + 8;
-    double* sacc = reinterpret_cast<double*>(after_ring + 128);  // [NV][NT]
+    double* sacc = reinterpret_cast<double*>(after_ring + 128);  // [NV][NT / 2]: lanes 2k and 2k+1 share a slot (owned by the even lane),
+                                                                 // which buys the ring a fourth stage
 #ifdef MCP_DEBUG_BOUNDS
     if (threadIdx.x < MCP_DBG_CANARY_BYTES / 4) reinterpret_cast<unsigned int*>(after_ring - MCP_DBG_CANARY_BYTES)[threadIdx.x] = MCP_DBG_CANARY;
 #endif
@@ -393,7 +399,8 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
         // the terminal step reads no carry: its tiles can fly before anything else happens
         while (cs.n < n_stages && cs.n < my_tiles) { issue_slab(); issue_carry(); }
     }
-    for (int m = 0; m < NV; ++m) sacc[m * NT + tid] = 0.0;
+    for (int m = 0; m < NV; ++m)
+        if (!(tid & 1)) sacc[m * (NT / 2) + (tid >> 1)] = 0.0;
 
     // ---- phase 0: sample sums of rows w, w + nw, ... over the first ns paths (lsm_scale_sums) ----
     for (int j = w; j < M; j += nw) {
@@ -522,7 +529,9 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
             if (++since == FLUSH) {
 #pragma unroll
                 for (int m = 0; m < NV; ++m) {
-                    sacc[m * NT + tid] += (double)(la[m].x + la[m].y);
+                    float v = la[m].x + la[m].y;
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (!(tid & 1)) sacc[m * (NT / 2) + (tid >> 1)] += (double)v;
                     la[m] = make_float2(0.f, 0.f);
                 }
                 since = 0;
@@ -544,9 +553,10 @@ __device__ void worker(const Args& a, unsigned char* smem_raw) {
             // ---- this worker's row of the step: warp sums -> 16 rows in shared memory -> thread m adds them in warp order ----
 #pragma unroll
             for (int m = 0; m < NV; ++m) {
-                const double t = warp_sum(sacc[m * NT + tid] + (double)(la[m].x + la[m].y) + (m == 0 ? (double)cnt : 0.0));
+                const double mine = (tid & 1) ? 0.0 : sacc[m * (NT / 2) + (tid >> 1)];
+                const double t = warp_sum(mine + (double)(la[m].x + la[m].y) + (m == 0 ? (double)cnt : 0.0));
                 if (lane == 0) red[warp][m] = t;
-                sacc[m * NT + tid] = 0.0;
+                if (!(tid & 1)) sacc[m * (NT / 2) + (tid >> 1)] = 0.0;
                 la[m] = make_float2(0.f, 0.f);
             }
             since = 0;

@@ -81,11 +81,97 @@ static __device__ __noinline__ void solve_fallback_jacobi(double* G /*[n][MAXP+1
     }
 }
 
+// The reference solves  [1, S, .., S^p] c = y  with Eigen's bdcSvd().solve (LSMPricer.cpp:61-76): a min-norm solve that DROPS
+// the singular directions of the RAW monomial design with sigma_i < sigma_max * min(rows, cols) * eps (SVDBase::rank()).
+// For p >= 5 and S ~ 100 that cut really bites (sigma_min / sigma_max ~ 4e-15 at p = 5, 6e-18 at p = 6), so a full-rank
+// fit in the standardised basis is NOT what the reference returns.  The cut can be reproduced without ever forming the
+// raw design:  with G = L L^T the Cholesky factor of the standardised Gram matrix and  r(S) = M u(x)  the (exact,
+// lower-triangular) change of basis from the standardised monomials u to the raw ones,
+//     A_raw = Q B,   Q = U L^{-T} (orthonormal columns),   B = L^T M^T  (upper triangular, column-graded like Eigen's R),
+// so A_raw and the small matrix B share their singular values and  c = L^{-T} P z,  z = L^{-1} X^T y,  P = projector onto the
+// left singular vectors of B that survive the reference's cut.  One-sided (Hestenes) Jacobi on the columns of B is
+// accurate for column-graded matrices -- it is what the CPU oracle (and Eigen, below 16 columns) runs on R.  Full rank
+// (every realistic case for p <= 4) leaves z untouched, bit for bit.
+struct RefRank {
+    double mu, inv_s;  // standardisation of the step being regressed: x = (S - mu) * inv_s
+};
+
+template <int P>
+static __device__ __noinline__ void project_onto_reference_rank(const double (&L)[P + 1][P + 1], const double (&d)[P + 1], const RefRank& rr, double count,
+                                                                double (&z)[P + 1]) {
+    constexpr int n = P + 1;
+    const double s = 1.0 / rr.inv_s;
+    // M[k][j] = C(k, j) mu^(k-j) s^j  (S^k = (mu + s x)^k), lower triangular
+    double M[n][n];
+    for (int k = 0; k < n; ++k) {
+        double binom = 1.0;
+        for (int j = 0; j <= k; ++j) {
+            double v = binom;
+            for (int q = 0; q < k - j; ++q) v *= rr.mu;
+            for (int q = 0; q < j; ++q) v *= s;
+            M[k][j] = v;
+            binom = binom * (double)(k - j) / (double)(j + 1);
+        }
+        for (int j = k + 1; j < n; ++j) M[k][j] = 0.0;
+    }
+    // B = L^T D^{-1} M^T with the stored factor of the EQUILIBRATED Gram matrix: L_full[k][a] = (k == a ? 1 / L[k][k] : L[k][a]), D = diag(d)
+    double W[n][n];
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            double acc = 0.0;
+            for (int k = a; k <= b; ++k) acc += (k == a ? 1.0 / L[k][k] : L[k][a]) / d[k] * M[b][k];
+            W[a][b] = acc;
+        }
+    // one-sided Jacobi: rotate column pairs until mutually orthogonal; the columns end up as sigma_i w_i
+    bool rotated = true;
+    for (int sweep = 0; sweep < 60 && rotated; ++sweep) {
+        rotated = false;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                double a = 0.0, bb = 0.0, c = 0.0;
+                for (int i = 0; i < n; ++i) { a += W[i][p] * W[i][p]; bb += W[i][q] * W[i][q]; c += W[i][p] * W[i][q]; }
+                if (c == 0.0 || fabs(c) <= 2.220446049250313e-16 * sqrt(a * bb)) continue;
+                rotated = true;
+                const double zeta = (bb - a) / (2.0 * c);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (int i = 0; i < n; ++i) {
+                    const double wp = W[i][p], wq = W[i][q];
+                    W[i][p] = cs * wp - sn * wq;
+                    W[i][q] = sn * wp + cs * wq;
+                }
+            }
+    }
+    double sig[n], smax = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += W[i][j] * W[i][j];
+        sig[j] = sqrt(t);
+        smax = fmax(smax, sig[j]);
+    }
+    const double diag = count < (double)n ? count : (double)n;                // Eigen: min(rows, cols)
+    double thr = smax * diag * 2.220446049250313e-16;                         // SVDBase::rank(): keep sigma_i >= this
+    if (thr < 2.2250738585072014e-308) thr = 2.2250738585072014e-308;
+    bool all = true;
+    for (int j = 0; j < n; ++j) all = all && (sig[j] >= thr && sig[j] > 0.0);
+    if (all) return;                                                           // full rank: z stays as it is, bit for bit
+    double zp[n];
+    for (int i = 0; i < n; ++i) zp[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        if (!(sig[j] >= thr && sig[j] > 0.0)) continue;
+        double proj = 0.0;
+        for (int i = 0; i < n; ++i) proj += W[i][j] * z[i];
+        proj /= sig[j] * sig[j];
+        for (int i = 0; i < n; ++i) zp[i] += W[i][j] * proj;
+    }
+    for (int i = 0; i < n; ++i) z[i] = zp[i];
+}
+
 // Solve the normal equations of one step from the (globally reduced) moments -> coef row (one thread).
 //   G[a][b] = s[a+b], rhs[a] = t[a].  Diagonal equilibration; Cholesky when safely positive definite (unrolled,
-//   in registers), else the Jacobi fallback above.
+//   in registers), else the Jacobi fallback above.  rr != nullptr: apply the reference's rank cut (see above).
 template <int P>
-__device__ __forceinline__ void solve_normal_equations(const double* mom, double* __restrict__ coef_row) {
+__device__ __forceinline__ void solve_normal_equations(const double* mom, double* __restrict__ coef_row, const RefRank* rr = nullptr) {
     constexpr int n = P + 1;
     double G[n][n], rhs[n], d[n], z[n], L[n][n];
 #pragma unroll
@@ -124,6 +210,7 @@ __device__ __forceinline__ void solve_normal_equations(const double* mom, double
             for (int m = 0; m < i; ++m) sacc -= L[i][m] * z[m];
             z[i] = sacc * L[i][i];
         }
+        if (rr != nullptr && P >= 1) project_onto_reference_rank<P>(L, d, *rr, mom[0], z);
 #pragma unroll
         for (int i = n - 1; i >= 0; --i) {
             double sacc = z[i];
@@ -144,15 +231,14 @@ __device__ __forceinline__ void solve_normal_equations(const double* mom, double
     for (int a = 0; a < n; ++a) coef_row[a] = z[a] * d[a];
 }
 
-static __device__ __noinline__ void solve_dispatch(const double* mom, int p, double* coef_row) {
+static __device__ __noinline__ void solve_dispatch(const double* mom, int p, double* coef_row, const RefRank* rr = nullptr) {
     switch (p) {
-        case 0: solve_normal_equations<0>(mom, coef_row); break;
-        case 1: solve_normal_equations<1>(mom, coef_row); break;
-        case 2: solve_normal_equations<2>(mom, coef_row); break;
-        case 3: solve_normal_equations<3>(mom, coef_row); break;
-        case 4: solve_normal_equations<4>(mom, coef_row); break;
-        case 5: solve_normal_equations<5>(mom, coef_row); break;
-        default: solve_normal_equations<6>(mom, coef_row); break;
+        case 0: solve_normal_equations<0>(mom, coef_row, rr); break;
+        case 1: solve_normal_equations<1>(mom, coef_row, rr); break;
+        case 2: solve_normal_equations<2>(mom, coef_row, rr); break;
+        case 3: solve_normal_equations<3>(mom, coef_row, rr); break;
+        case 4: solve_normal_equations<4>(mom, coef_row, rr); break;
+        case 5: solve_normal_equations<5>(mom, coef_row, rr); break;
+        default: solve_normal_equations<6>(mom, coef_row, rr); break;
     }
 }
-

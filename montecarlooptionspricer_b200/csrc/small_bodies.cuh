@@ -117,7 +117,8 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
         }
         sb_sum<NV>(acc, mom);
         if (tid == 0) {
-            solve_normal_equations<P>(mom, cf);                                               // :76
+            const RefRank rr{mu, inv_s};
+            solve_normal_equations<P>(mom, cf, &rr);                                          // :76 (with Eigen's rank cut, lsm_solve.cuh)
             if (coef_out)
                 for (int k = 0; k < COEF_LD; ++k) coef_out[(int64_t)j * COEF_LD + k] = cf[k];
         }

@@ -45,20 +45,31 @@ def test_lsm_config1_put_parity(engine, port, p):
         assert 6.0 < got.price < 6.2
 
 
-def test_lsm_high_order_is_outside_the_reference_parity_domain(engine, port):
-    """For polyOrder >= 5 the reference's RAW monomial design [1,S,..,S^p] with S~100 is numerically rank
-    deficient by Eigen's own rule (sigma_min < (p+1) eps sigma_max), so bdcSvd().solve() silently drops
-    directions (LSMPricer.cpp:76) and the result hinges on rounding of sub-threshold singular values.  The
-    device regresses in a standardised basis and keeps full rank; there the agreement is statistical."""
-    paths = gbm_paths(port, 100_000, 50, seed=1)
-    S = paths[:, 10]
-    sv = np.linalg.svd(np.vander(S[S < 100.0], 6, increasing=True), compute_uv=False)
-    assert sv[-1] < 6 * np.finfo(float).eps * sv[0]  # the reference truncates here
-    ps = engine.upload_paths(paths, dtype=m.MCP_F32)
-    got = engine.lsm_price(ps, 0.05, 100.0, 1.0, 0.02, False, 5)
-    want = port.lsm(paths, 0.05, 100.0, 1.0, 0.02, False, 5)
-    assert abs(got.price - want["price"]) < 3 * want["stderr"]
-    ps.close()
+@pytest.mark.parametrize("p,n_paths,n", [(5, 100_000, 50), (6, 100_000, 50), (5, 20_000, 50), (6, 20_000, 50), (6, 250, 62), (5, 300_000, 20)])
+def test_lsm_high_order_reproduces_the_reference_rank_cut(engine, port, monkeypatch, p, n_paths, n):
+    """For polyOrder >= 5 the reference's RAW monomial design [1,S,..,S^p] with S~100 is numerically rank deficient by Eigen's
+    own rule (sigma_min < min(rows, cols) eps sigma_max), so bdcSvd().solve() drops directions (LSMPricer.cpp:76).  The device
+    regresses in a standardised basis, where nothing is deficient, and re-creates that cut from the Cholesky factor and the
+    exact change of basis (lsm_solve.cuh): same exercise indices, same price.  Without the cut the full-rank fit is a different
+    (better conditioned) estimator that agrees with the reference only statistically."""
+    paths = gbm_paths(port, n_paths, n, seed=p + n_paths)
+    got, want = check_parity(engine, port, paths, 0.05, 100.0, 1.0, 1.0 / n, False, p, price_tol=2e-9)
+    if n_paths >= 20_000:
+        S = paths[:, n // 5]
+        sv = np.linalg.svd(np.vander(S[S < 100.0], p + 1, increasing=True), compute_uv=False)
+        if sv[-1] < (p + 1) * np.finfo(float).eps * sv[0]:          # the reference truncates at this step: the cut must matter
+            monkeypatch.setenv("MCP_LSM_REF_RANK", "0")
+            ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+            full = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / n, False, p, carry=m.MCP_F64)
+            ps.close()
+            assert abs(full.price - want["price"]) > 1e-7 * want["price"]          # not the reference's estimator ...
+            assert abs(full.price - want["price"]) < 4 * want["stderr"]             # ... but a statistically equivalent one
+    if n_paths > 4096:  # throughput mode takes the same cut for p >= 5
+        monkeypatch.delenv("MCP_LSM_REF_RANK", raising=False)
+        ps = engine.upload_paths(paths, dtype=m.MCP_F32)
+        fast = engine.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / n, False, p, carry=m.MCP_F32)
+        ps.close()
+        assert abs(fast.price - want["price"]) < 1e-5 * want["price"]
 
 
 def test_lsm_fitted_continuation_matches_oracle(engine, port):

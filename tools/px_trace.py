@@ -53,5 +53,41 @@ def main():
     eng.close()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("PX_TRACE_WORKERS"):
     main()
+
+
+def per_worker(k=26):
+    """Which workers are slow, and are they the same ones every step?  Prints the distribution of per-worker mean stream time."""
+    os.environ["MCP_PX_TRACE"] = "1"
+    os.environ["MCP_SWEEP_IMPL"] = "4"
+    eng = m.Engine(0)
+    L = eng._L
+    L.mcp_debug_px_trace.restype = C.c_int64
+    L.mcp_debug_px_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    ps = eng.pathset(1 << k, 252)
+    eng.gen_rbergomi(ps, 100.0, 0.05, 0.04, 0.1, 1.9, -0.9, 1.0 / 252.0, seed=3)
+    for _ in range(2):
+        eng.lsm_price(ps, 0.05, 100.0, 1.0, 1.0 / 252.0, False, 3, carry=m.MCP_F32)
+    rows, cols = C.c_int(), C.c_int()
+    n = L.mcp_debug_px_trace(eng._h, None, 0, C.byref(rows), C.byref(cols))
+    buf = np.zeros(n, dtype=np.uint64)
+    L.mcp_debug_px_trace(eng._h, buf.ctypes.data_as(C.c_void_p), n, None, None)
+    t = buf.reshape(rows.value, cols.value, 4).astype(np.float64) * 1e-3
+    wk = t[2:-2, 1:, :]
+    dur = wk[:, :, 1] - wk[:, :, 0]            # [step][worker]
+    mean_w = dur.mean(axis=0)
+    order = np.argsort(mean_w)
+    print(f"2^{k}: per-worker mean stream time: min {mean_w.min():.2f} p10 {np.percentile(mean_w, 10):.2f} median {np.median(mean_w):.2f} "
+          f"p90 {np.percentile(mean_w, 90):.2f} max {mean_w.max():.2f} us; per-step max/median {np.median(dur.max(axis=1) / np.median(dur, axis=1)):.3f}")
+    print("   slowest workers:", [(int(w), round(float(mean_w[w]), 2)) for w in order[-8:]], " fastest:", [(int(w), round(float(mean_w[w]), 2)) for w in order[:6]])
+    # how persistent is the ranking: correlation of a worker's time in even vs odd steps
+    a, b = dur[0::2].mean(axis=0), dur[1::2].mean(axis=0)
+    print(f"   even/odd-step correlation of per-worker means: {np.corrcoef(a, b)[0, 1]:.3f}; per-step noise (std over steps of one worker, median): "
+          f"{np.median(dur.std(axis=0)):.2f} us")
+    ps.close()
+    eng.close()
+
+
+if __name__ == "__main__" and os.environ.get("PX_TRACE_WORKERS"):
+    per_worker(int(os.environ["PX_TRACE_WORKERS"]))
