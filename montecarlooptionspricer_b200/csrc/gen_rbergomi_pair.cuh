@@ -32,6 +32,19 @@
 
 constexpr int PAIR_SMEM = 2 * 256 * 32 * 4 + 16 * 64 * 4 + 256 * 8 + 256 * (int)sizeof(Tw) + 256 * 8;
 
+// predicated 8-byte store: the guard becomes a predicate on the STG, never a branch (a branch per time index splits phase 3
+// into sixteen basic blocks and keeps the scheduler from overlapping the SFU work of one row with the stores of the last)
+__device__ __forceinline__ void st2_if(float* p, float2 v, bool ok) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.global.v2.f32 [%0], {%1, %2}; }" ::"l"(p), "f"(v.x), "f"(v.y), "r"((int)ok) : "memory");
+}
+
+// Scheduling (r02; same stream and bits as the first version, 49.8 -> 45.5 ms at 2^26 x 252): the kernel alternates between
+// integer-multiply-bound stretches (Philox: IMAD.WIDE on the FMA-heavy pipe) and SFU-bound stretches (Box-Muller, ex2),
+// and the two pipes run side by side when fed (tools/microbench/pipes.cu: MUFU + IMAD.WIDE cost max, not sum).  So every
+// phase is ONE straight-line block in which a Philox batch is drawn one step ahead of the Box-Muller work that consumes
+// the previous one; the first spectral batch of the NEXT tile is drawn under the ex2 / store work of phase 3; the
+// `m < n` guards of the second DFT pass are gone (rows >= n are never stored and only reach chunk totals that no stored
+// row uses) and full tiles store through predicated STGs instead of a branch per time index.
 template <bool DUMP>
 __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParams P, PhiloxKeys K, const float2* __restrict__ g_phis,
                                                                         const float* __restrict__ g_sw, const float2* __restrict__ g_tw,
@@ -64,6 +77,16 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
     const bool even_rows = ((P.ld & 1) == 0) && ((P.path_offset & 1) == 0);  // 8-byte stores need even local ids and row stride
     __syncthreads();
 
+    // the first spectral Philox batch of a tile is drawn one tile ahead, under the SFU / store work of phase 3
+    uint4 cur[4];
+    auto draw_first = [&](uint64_t Tn) {
+        const uint64_t fn = (Tn << 5) + (uint64_t)col;
+        const uint32_t n0 = (uint32_t)fn, n1 = (uint32_t)(fn >> 32), c2 = (uint32_t)(k0 >> 1);
+        cur[0] = philox4x32_10(n0, n1, c2, 4u, K); cur[1] = philox4x32_10(n0 | 1u, n1, c2, 4u, K);
+        cur[2] = philox4x32_10(n0, n1, c2 + 1u, 4u, K); cur[3] = philox4x32_10(n0 | 1u, n1, c2 + 1u, 4u, K);
+    };
+    draw_first(T0 + (uint64_t)blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t T = T0 + (uint64_t)tile;
         const uint64_t gidA = (T << 6) + (uint64_t)col, gidB = gidA + 32;   // first path of the Re pair / of the Im pair
@@ -74,21 +97,33 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
         const uint32_t f0 = (uint32_t)fid, f1 = (uint32_t)(fid >> 32);
 
         // ---- phase 1: spectral normals, in_m = sqrt(w_m) G_m ------------------------------------------------
-#pragma unroll 1
-        for (int kq = 0; kq < 16; kq += 4) {
-            const int m0 = k0 + kq;
-            float2 zr[4], zi[4];
-            const uint4 xa0 = philox4x32_10(f0, f1, (uint32_t)(m0 >> 1), 4u, K), xa1 = philox4x32_10(f0 | 1u, f1, (uint32_t)(m0 >> 1), 4u, K);
-            const uint4 xb0 = philox4x32_10(f0, f1, (uint32_t)(m0 >> 1) + 1u, 4u, K), xb1 = philox4x32_10(f0 | 1u, f1, (uint32_t)(m0 >> 1) + 1u, 4u, K);
-            box_muller_x2(xa0.x, xa0.y, xa1.x, xa1.y, zr[0], zi[0]);
-            box_muller_x2(xa0.z, xa0.w, xa1.z, xa1.w, zr[1], zi[1]);
-            box_muller_x2(xb0.x, xb0.y, xb1.x, xb1.y, zr[2], zi[2]);
-            box_muller_x2(xb0.z, xb0.w, xb1.z, xb1.w, zr[3], zi[3]);
+        {
+            // software pipeline: the integer rounds of batch q + 1 have no dependence on the SFU chain of batch q, so inside
+            // one straight-line block the scheduler runs IMAD.WIDE / LOP3 under MUFU latency instead of after it
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 s = sw[m0 + t];
-                Rc[(kq + t) * RS] = f2mul(zr[t], s);
-                Ic[(kq + t) * RS] = f2mul(zi[t], s);
+            for (int kq = 0; kq < 16; kq += 4) {
+                const int m0 = k0 + kq;
+                uint4 nxt[4];
+                if (kq + 4 < 16) {
+                    const uint32_t c2 = (uint32_t)((m0 + 4) >> 1);
+                    nxt[0] = philox4x32_10(f0, f1, c2, 4u, K); nxt[1] = philox4x32_10(f0 | 1u, f1, c2, 4u, K);
+                    nxt[2] = philox4x32_10(f0, f1, c2 + 1u, 4u, K); nxt[3] = philox4x32_10(f0 | 1u, f1, c2 + 1u, 4u, K);
+                }
+                float2 zr[4], zi[4];
+                box_muller_x2(cur[0].x, cur[0].y, cur[1].x, cur[1].y, zr[0], zi[0]);
+                box_muller_x2(cur[0].z, cur[0].w, cur[1].z, cur[1].w, zr[1], zi[1]);
+                box_muller_x2(cur[2].x, cur[2].y, cur[3].x, cur[3].y, zr[2], zi[2]);
+                box_muller_x2(cur[2].z, cur[2].w, cur[3].z, cur[3].w, zr[3], zi[3]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 s = sw[m0 + t];
+                    Rc[(kq + t) * RS] = f2mul(zr[t], s);
+                    Ic[(kq + t) * RS] = f2mul(zi[t], s);
+                }
+                if (kq + 4 < 16) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) cur[t] = nxt[t];
+                }
             }
         }
         __syncthreads();
@@ -120,6 +155,13 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
         }
 
         // ---- phase 2a: DIF pass 1 on column g: elements g + 16 q, output s scaled by w256^{g s} -------------------
+        const uint32_t a0 = (uint32_t)gidA, a1 = (uint32_t)(gidA >> 32), b0 = (uint32_t)gidB, b1 = (uint32_t)(gidB >> 32);
+        uint4 wq[4];  // Brownian Philox batch q of phase 2b
+        auto draw_w = [&](int q) {
+            const uint32_t ctr = (uint32_t)(4 * g + q);
+            wq[0] = philox4x32_10(a0, a1, ctr, 6u, K); wq[1] = philox4x32_10(a0 | 1u, a1, ctr, 6u, K);
+            wq[2] = philox4x32_10(b0, b1, ctr, 6u, K); wq[3] = philox4x32_10(b0 | 1u, b1, ctr, 6u, K);
+        };
         {
             float2* ar = reinterpret_cast<float2*>(Are + g * TC + col);
             float2* ai = reinterpret_cast<float2*>(Aim + g * TC + col);
@@ -148,12 +190,10 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
             x2_dft16_transposed(x);
             float2* oa = reinterpret_cast<float2*>(Are + g * TC + col);
             float2* ob = reinterpret_cast<float2*>(Aim + g * TC + col);
-            const uint32_t a0 = (uint32_t)gidA, a1 = (uint32_t)(gidA >> 32), b0 = (uint32_t)gidB, b1 = (uint32_t)(gidB >> 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t ctr = (uint32_t)(4 * g + q);
-                const uint4 xA0 = philox4x32_10(a0, a1, ctr, 6u, K), xA1 = philox4x32_10(a0 | 1u, a1, ctr, 6u, K);
-                const uint4 xB0 = philox4x32_10(b0, b1, ctr, 6u, K), xB1 = philox4x32_10(b0 | 1u, b1, ctr, 6u, K);
+                draw_w(q);
+                const uint4 xA0 = wq[0], xA1 = wq[1], xB0 = wq[2], xB1 = wq[3];
                 float2 wA[4], wB[4];
                 box_muller_x2(xA0.x, xA0.y, xA1.x, xA1.y, wA[0], wA[1]);
                 box_muller_x2(xA0.z, xA0.w, xA1.z, xA1.w, wA[2], wA[3]);
@@ -167,8 +207,9 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
                     const float2 uA0 = f2fma(f2add(x[x2_slot(s)].re, cm), half2v, lsq2), uB0 = f2fma(f2add(x[x2_slot(s)].im, cm), half2v, lsq2);
                     const float2 uA = make_float2(fast_ex2(uA0.x), fast_ex2(uA0.y));  // sqrt(v) sqrt(dt) log2e, see log2_increment()
                     const float2 uB = make_float2(fast_ex2(uB0.x), fast_ex2(uB0.y));
-                    oa[s * 16 * RS] = in ? f2fma(uA, f2fma(uA, nkq2, wA[t]), rd22) : f2splat(0.f);
-                    ob[s * 16 * RS] = in ? f2fma(uB, f2fma(uB, nkq2, wB[t]), rd22) : f2splat(0.f);
+                    // rows >= n: finite, never stored, and they only reach chunk totals that no stored row uses
+                    oa[s * 16 * RS] = f2fma(uA, f2fma(uA, nkq2, wA[t]), rd22);
+                    ob[s * 16 * RS] = f2fma(uB, f2fma(uB, nkq2, wB[t]), rd22);
                     if (DUMP && in) {  // the reference's W1 / W2 slots: rho W1 + sqrt(1 - rho^2) W2 = w
                         float* d1 = draws_out + (int64_t)(2 * n + m) * P.ld_draws;
                         float* d2 = draws_out + (int64_t)(3 * n + m) * P.ld_draws;
@@ -205,6 +246,19 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
             }
             const bool bothA = even_rows && liveA0 && liveA1, bothB = even_rows && liveB0 && liveB1;
             float* o = out + (int64_t)(k0 + 1) * P.ld + locA;
+            if (bothA && bothB) {  // the whole tile is inside the shard (all but the edge tiles): no branch per row
+                const int rows = n - k0;       // rows of this chunk that exist (>= 16 for all chunks but the last)
+                draw_first(T + (uint64_t)gridDim.x);
+#pragma unroll
+                for (int t = 0; t < 16; ++t, o += P.ld) {
+                    const float2 a = f2add(offa, ca[t]), b = f2add(offb, cb[t]);
+                    const float2 sa = f2mul(S02, make_float2(fast_ex2(a.x), fast_ex2(a.y)));
+                    const float2 sb = f2mul(S02, make_float2(fast_ex2(b.x), fast_ex2(b.y)));
+                    st2_if(o, sa, t < rows);
+                    st2_if(o + 32, sb, t < rows);
+                }
+            } else {
+            draw_first(T + (uint64_t)gridDim.x);
 #pragma unroll
             for (int t = 0; t < 16; ++t, o += P.ld) {
                 if (k0 + t < n) {
@@ -216,6 +270,7 @@ __global__ void __launch_bounds__(NT2, 2) rbergomi_paths_n256pair_kernel(RbParam
                     if (bothB) *reinterpret_cast<float2*>(o + 32) = sb;
                     else { if (liveB0) o[32] = sb.x; if (liveB1) o[33] = sb.y; }
                 }
+            }
             }
         }
         // no barrier needed here: the next tile's phase 1 writes only chunk g of re / im (read by this thread alone in

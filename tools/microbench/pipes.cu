@@ -1,5 +1,6 @@
 // pipes.cu -- issue-rate microbenchmark for the instruction classes the generator leans on (B200, sm_100a):
-// FFMA, FFMA2 (packed fp32x2), IMAD.WIDE.U32, LOP3, MUFU.EX2, and FFMA2 + IMAD.WIDE mixed.
+// FFMA, FFMA2 (packed fp32x2), IMAD.WIDE.U32, LOP3, MUFU.EX2, and FFMA2 + IMAD.WIDE mixed,
+// and MUFU mixed with each of them (does the SFU pipe run beside the FMA-heavy pipe, or do they share a dispatch port?).
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a pipes.cu -o pipes && ./pipes
 #include <cstdio>
 #include <cstdint>
@@ -26,6 +27,12 @@ __global__ void __launch_bounds__(256) k(float* out, uint32_t seed) {
             if (KIND == 4) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); }
             if (KIND == 5) { b[i] = __ffma2_rn(b[i], m2, d2); w[i] = (unsigned long long)0xD2511F53u * (uint32_t)w[i] + (w[i] >> 32); }
             if (KIND == 6) { a[i] = fmaf(a[i], m, d); w[i] = (unsigned long long)0xD2511F53u * (uint32_t)w[i] + (w[i] >> 32); }
+            if (KIND == 7) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); w[i] = (unsigned long long)0xD2511F53u * (uint32_t)w[i] + (w[i] >> 32); }
+            if (KIND == 8) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); b[i] = __ffma2_rn(b[i], m2, d2); }
+            if (KIND == 9) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); c[i] = (c[i] ^ (c[i] >> 3)) ^ seed; }
+            if (KIND == 10) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); w[i] = (unsigned long long)0xD2511F53u * (uint32_t)w[i] + (w[i] >> 32);
+                              w[(i + 1) % ILP] = (unsigned long long)0xCD9E8D57u * (uint32_t)w[(i + 1) % ILP] + (w[(i + 1) % ILP] >> 32); }
+            if (KIND == 11) { a[i] = (float)c[i] * m; c[i] += seed; }
         }
     }
     float s = 0.f;
@@ -61,5 +68,10 @@ int main() {
     run<4>("MUFU.EX2", 1);
     run<5>("FFMA2 + IMAD.WIDE", 2);
     run<6>("FFMA + IMAD.WIDE", 2);
+    run<7>("MUFU.EX2 + IMAD.WIDE", 2);
+    run<8>("MUFU.EX2 + FFMA2", 2);
+    run<9>("MUFU.EX2 + LOP3 x2", 3);
+    run<10>("MUFU.EX2 + 2 IMAD.WIDE", 3);
+    run<11>("I2FP.U32 + FMUL + IADD", 3);
     return 0;
 }

@@ -1,6 +1,9 @@
 """Turn the ncu artefacts of a gpurun call (gpurun_out/) into the small tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <gen.ncu-rep> <sweep.ncu-rep>
+    python tools/summarize_profiles.py <round-tag> <launches.csv> <title>=<report.ncu-rep> ... [--out DIR]
+
+Runs where the reports are (on the GPU box, inside the gpurun call: the reports themselves are too large to travel back)
+and writes <DIR>/<round-tag>_summary.md (default DIR = profiles/).
 """
 import collections
 import csv
@@ -77,20 +80,30 @@ def launches(path):
 
 
 def main():
-    tag, launch_csv, gen_rep, sweep_rep = sys.argv[1:5]
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    argv = sys.argv[1:]
+    out_dir = os.path.join(ROOT, "profiles")
+    if "--out" in argv:
+        k = argv.index("--out")
+        out_dir = argv[k + 1]
+        del argv[k:k + 2]
+    tag, launch_csv, reps = argv[0], argv[1], [a.split("=", 1) for a in argv[2:]]
+    os.makedirs(out_dir, exist_ok=True)
     lines = [f"# ncu summary {tag}", ""]
-    agg = launches(launch_csv)
-    total = sum(v[1] for v in agg.values())
-    lines += [f"## launch list ({os.path.basename(launch_csv)}; cold-cache, serialised: compare SHARES)", "",
-              "| kernel | launches | total us | share | avg us |", "|---|---|---|---|---|"]
-    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"| {name} | {n} | {us:.1f} | {100 * us / total:.1f}% | {us / n:.2f} |")
-    lines.append("")
-    for title, rep in (("generator", gen_rep), ("LSM sweep", sweep_rep)):
+    if os.path.exists(launch_csv):
+        agg = launches(launch_csv)
+        total = sum(v[1] for v in agg.values())
+        lines += [f"## launch list ({os.path.basename(launch_csv)}; cold-cache, serialised: compare SHARES)", "",
+                  "| kernel | launches | total us | share | avg us |", "|---|---|---|---|---|"]
+        for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            lines.append(f"| {name} | {n} | {us:.1f} | {100 * us / total:.1f}% | {us / n:.2f} |")
+        lines.append("")
+    for title, rep in reps:
+        if not os.path.exists(rep):
+            lines += [f"## {title}: capture missing ({os.path.basename(rep)})", ""]
+            continue
         ms = raw_metrics(rep)
         lines += [f"## {title}: `ncu --set full` ({os.path.basename(rep)})", ""]
-        for d in ms[:2]:
+        for d in ms[:3]:
             lines.append(f"### {d.get('kernel', '?')[:120]}")
             lines.append("")
             lines.append("| metric | value |")
@@ -106,7 +119,7 @@ def main():
         lines.append("")
         lines.append("executed warp instructions by opcode: " + ", ".join(f"{o} {100 * v / e:.1f}%" for o, v in ops.most_common(14)))
         lines.append("")
-    out = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
+    out = os.path.join(out_dir, f"{tag}_summary.md")
     open(out, "w").write("\n".join(lines) + "\n")
     print(out)
 
