@@ -437,6 +437,10 @@ int mcp_kernel_config(mcp_ctx* ctx, const void* kernel, int block, size_t smem, 
 
 int mcp_scratch_reserve(mcp_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MCP_OK;
+    // grow geometrically and in whole MiB: a caller that walks through growing sizes (the maturities of a surface) would
+    // otherwise pay a stream synchronisation + cudaFree + cudaMalloc at every step
+    if (bytes < 2 * ctx->scratch_bytes) bytes = 2 * ctx->scratch_bytes;
+    bytes = (bytes + ((size_t)1 << 20) - 1) >> 20 << 20;
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->scratch) cudaFree(ctx->scratch);
     ctx->scratch = nullptr;

@@ -551,6 +551,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// blocking wait with a suspend-time hint: the thread sleeps in hardware until the phase flips (or the hint expires) instead
+// of spinning through issue slots that the other warps of the scheduler could use
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
                  "r"(smem_u32(bar))
@@ -891,16 +899,32 @@ inline SweepFn2Fwd pick_sweep_tma64(int p) {
 
 // ---------------------------------------------------------------------------------------------------------
 // sweep(j) for SEVERAL CONTRACTS ON THE SAME PATHS (strike ladder of a surface, BASELINE config 5): one warp per
-// contract.  The slab tiles S_j | S_{j-1} are fetched once per CTA by the TMA ring and read by all warps from shared
-// memory; the ring also carries every contract's carry tile, each consumed by its own warp.  Per path-step that is 8 B of slab + 8 B of carry per
-// contract instead of 16 B per contract, and the per-launch fixed cost (launch, fold, solve) is paid once for the
-// whole ladder.  Same packed fp32 arithmetic and the same per-contract standardisation as the single-contract
-// throughput kernels.  The last CTA folds the per-CTA moment rows of every contract in a fixed order; warp c solves contract c.
+// contract.  Per path-step that is 8 B of slab shared by the whole ladder + 8 B of carry per contract instead of 16 B per
+// contract, and the per-launch fixed cost (launch, fold, solve) is paid once for the ladder.  Same packed fp32 arithmetic
+// and the same per-contract standardisation as the single-contract throughput kernels.
+//
+// Data movement (r02; the first version moved whole 18-array stages of 72 KB, two of which fit: 4.8 TB/s):
+//   * slab tiles S_j | S_{j-1} (1024 paths) stream through a deep shared ring, read by all sixteen contract warps from
+//     shared memory; a stage is refilled by WHICHEVER WARP LEAVES IT LAST (a shared-memory ticket per stage), so nobody
+//     ever waits for a hand-back;
+//   * every contract warp owns a PRIVATE ring of carry tiles, which it refills itself the moment it has its tile in
+//     registers -- no warp ever waits for another warp's carry, and a stage is held for half a tile of arithmetic only.
+// Warps drift apart by up to the slab ring's depth; nothing in the tile loop is block-wide.
+// The last CTA folds the per-CTA moment rows of every contract in a fixed order; warp c solves contract c.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int MULTI_MAXC = 16;                 // contracts per launch = warps per CTA
-constexpr int MULTI_TILE = 1024;               // paths per tile
-constexpr int MULTI_STAGE_FLOATS = (2 + MULTI_MAXC) * MULTI_TILE;  // S_j | S_{j-1} | V_0 .. V_15
-constexpr int MULTI_STAGE_BYTES = MULTI_STAGE_FLOATS * 4;
+constexpr int MULTI_MAXC = 16;                 // contracts per launch = consumer warps per CTA
+constexpr int MULTI_NT = MULTI_MAXC * 32;
+#ifndef MCP_MULTI_TILE
+#define MCP_MULTI_TILE 1024
+#define MCP_MULTI_NS 4
+#endif
+constexpr int MULTI_TILE = MCP_MULTI_TILE;     // paths per tile
+constexpr int MULTI_NS = MCP_MULTI_NS;         // slab ring depth (tiles)
+constexpr int MULTI_SLAB_STAGE_BYTES = 2 * MULTI_TILE * 4;
+constexpr int MULTI_CARRY_SLOT_BYTES = MULTI_TILE * 4;
+constexpr int MULTI_MAXD = 8;                  // carry ring depth per warp (upper bound; the host picks what fits)
+constexpr int MULTI_BAR_BYTES = (2 * MULTI_NS + MULTI_MAXC * MULTI_MAXD) * 8;  // fullS | tickets | fullV
+constexpr int MULTI_ACC_LANES = MULTI_MAXC * 8;  // fp64 accumulator columns: one per group of four lanes
 
 struct MultiArgs {
     const float* S;
@@ -919,16 +943,21 @@ struct MultiArgs {
 };
 
 template <int P>
-__global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs a, int n_stages) {
+__global__ void __launch_bounds__(MULTI_NT, 1) lsm_multi_kernel(MultiArgs a, int depth) {
     constexpr int NM = 3 * P + 2;
     constexpr int NV = NM > 2 ? NM : 2;
-    constexpr int FLUSH = 8;
-    constexpr int NT = MULTI_MAXC * 32;
+    constexpr int FLUSH_TILES = 8 / (MULTI_TILE / 256) > 0 ? 8 / (MULTI_TILE / 256) : 1;  // fp32 partials cover <= 64 paths per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* ring = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES);  // "stage filled" (TMA completes them)
-    uint64_t* empty = full + 8;                                                                        // "stage consumed": one arrival per warp
-    double* sacc = reinterpret_cast<double*>(smem_raw + (size_t)n_stages * MULTI_STAGE_BYTES + 128);  // [NV][NT]
+    float* slab = reinterpret_cast<float*>(smem_raw);                                                   // [MULTI_NS][2][TILE]
+    float* carry = reinterpret_cast<float*>(smem_raw + MULTI_NS * MULTI_SLAB_STAGE_BYTES);              // [MAXC][depth][TILE]
+    unsigned char* after = smem_raw + MULTI_NS * MULTI_SLAB_STAGE_BYTES + (size_t)MULTI_MAXC * depth * MULTI_CARRY_SLOT_BYTES + MCP_DBG_CANARY_BYTES;
+    uint64_t* fullS = reinterpret_cast<uint64_t*>(after);   // slab stage filled (bulk copies complete it)
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(fullS + MULTI_NS);  // warps that have left the stage (monotone; 16 per use)
+    uint64_t* fullV = fullS + 2 * MULTI_NS;                  // [MAXC][MAXD] carry slot filled
+    double* sacc = reinterpret_cast<double*>(after + MULTI_BAR_BYTES);  // [NV][MULTI_ACC_LANES]
+#ifdef MCP_DEBUG_BOUNDS
+    if (threadIdx.x < MCP_DBG_CANARY_BYTES / 4) reinterpret_cast<unsigned int*>(after - MCP_DBG_CANARY_BYTES)[threadIdx.x] = MCP_DBG_CANARY;
+#endif
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;  // warp = contract
     const bool active = c < a.C;
     const int cc = active ? c : 0;
@@ -936,115 +965,165 @@ __global__ void __launch_bounds__(MULTI_MAXC * 32, 1) lsm_multi_kernel(MultiArgs
     const float* __restrict__ Sp = a.S + (int64_t)(a.j > 0 ? a.j - 1 : 0) * a.ld;
     float* __restrict__ V = a.V + (int64_t)cc * a.ld;
     const int mode = a.terminal ? 2 : a.kind[a.j];
-
-    // per-warp constants: this contract's strike, coefficients and standardisation
-    SweepArgs w;  // the view fast2_compute / fast2_load_consts expect
-    memset(&w, 0, sizeof(w));
-    w.n = a.n; w.j = a.j; w.do_moments = a.do_moments; w.do_final = a.do_final; w.is_call = a.is_call; w.disc = a.disc;
-    w.K = a.K[cc];
-    w.d.coef = a.coef + (int64_t)cc * a.M * COEF_LD;
-    w.d.mu = const_cast<double*>(a.mu) + (int64_t)cc * a.M;
-    w.d.inv_s = const_cast<double*>(a.inv_s) + (int64_t)cc * a.M;
-    w.g = make_stepk(w.K, w.disc, w.is_call);  // per warp = per contract, once per launch
-    FastConsts<P> k;
-    fast2_load_consts<P>(w, k);
-    float2 la[NV];
-    int cnt = 0;
-#pragma unroll
-    for (int m = 0; m < NV; ++m) { la[m] = make_float2(0.f, 0.f); sacc[m * NT + tid] = 0.0; }
+    const bool want_v = mode != 2;
 
     const int64_t ntile = (a.n + MULTI_TILE - 1) / MULTI_TILE;
-    const int64_t my_tiles = blockIdx.x < ntile ? (ntile - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int my_tiles = blockIdx.x < ntile ? (int)((ntile - 1 - blockIdx.x) / gridDim.x + 1) : 0;
     const uint64_t pol = l2_policy_evict_first();
-    auto tile_of = [&](int64_t it) -> int64_t {
-        const int64_t t = (int64_t)blockIdx.x + it * gridDim.x;
-        return (a.j & 1) ? (ntile - 1 - t) : t;
+    // first path of tile `it` of this CTA (serpentine over launches); all ring bookkeeping below is 32-bit counters --
+    // the loop runs once per 512 paths per warp, a 64-bit division there is a visible share of the instruction stream
+    const int64_t t_first = (a.j & 1) ? (ntile - 1 - (int64_t)blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t t_step = (a.j & 1) ? -(int64_t)gridDim.x : (int64_t)gridDim.x;
+    auto tile_of = [&](int it) -> int64_t { return t_first + (int64_t)it * t_step; };
+    auto tile_bytes = [&](int64_t i0) -> uint32_t {
+        const int64_t cnt = a.ld - i0 < MULTI_TILE ? a.ld - i0 : MULTI_TILE;  // rows are padded to ld (multiple of 128)
+        MCP_DBG_CHECK(i0 >= 0 && cnt > 0 && cnt <= MULTI_TILE && i0 + cnt <= a.ld && ((cnt * 4) & 15) == 0, DBG_RING_ISSUE);
+        return (uint32_t)cnt * 4u;
     };
-    auto issue = [&](int64_t it, int st) {  // one elected thread: the two slab tiles and every contract's carry tile
+    auto issue_slab = [&](int it, int st) {  // one elected lane
         const int64_t i0 = tile_of(it) * MULTI_TILE;
-        const int64_t cnt = a.ld - i0 < MULTI_TILE ? a.ld - i0 : MULTI_TILE;
-        const uint32_t bytes = (uint32_t)cnt * 4u;
-        float* dst = ring + (size_t)st * MULTI_STAGE_FLOATS;
-        MCP_DBG_CHECK(st >= 0 && st < n_stages && it >= 0 && it < my_tiles, DBG_RING_STAGE);
-        MCP_DBG_CHECK(i0 >= 0 && cnt > 0 && cnt <= MULTI_TILE && i0 + cnt <= a.ld && (bytes & 15u) == 0u && a.C >= 1 && a.C <= MULTI_MAXC, DBG_RING_ISSUE);
-        mbar_expect_tx(full + st, bytes * (1u + (a.do_moments ? 1u : 0u) + (mode != 2 ? (uint32_t)a.C : 0u)));
-        bulk_g2s_hint(dst, Sj + i0, bytes, full + st, pol);
-        if (a.do_moments) bulk_g2s(dst + MULTI_TILE, Sp + i0, bytes, full + st);
-        if (mode != 2)
-            for (int q = 0; q < a.C; ++q) bulk_g2s_hint(dst + (2 + q) * MULTI_TILE, a.V + (int64_t)q * a.ld + i0, bytes, full + st, pol);
+        const uint32_t bytes = tile_bytes(i0);
+        float* dst = slab + (size_t)st * (2 * MULTI_TILE);
+        MCP_DBG_CHECK(it >= 0 && it < my_tiles, DBG_RING_STAGE);
+        mbar_expect_tx(fullS + st, bytes * (a.do_moments ? 2u : 1u));
+        bulk_g2s_hint(dst, Sj + i0, bytes, fullS + st, pol);
+        if (a.do_moments) bulk_g2s(dst + MULTI_TILE, Sp + i0, bytes, fullS + st);  // read again as the next launch's S_j: default policy
+    };
+    auto issue_carry = [&](int it, int d) {  // lane 0 of an active contract warp: its own carry tile into its own ring
+        const int64_t i0 = tile_of(it) * MULTI_TILE;
+        const uint32_t bytes = tile_bytes(i0);
+        MCP_DBG_CHECK(it >= 0 && it < my_tiles && d < MULTI_MAXD && a.C >= 1 && a.C <= MULTI_MAXC, DBG_RING_STAGE);
+        mbar_expect_tx(fullV + c * MULTI_MAXD + d, bytes);
+        bulk_g2s_hint(carry + ((size_t)c * depth + d) * MULTI_TILE, V + i0, bytes, fullV + c * MULTI_MAXD + d, pol);
     };
     if (tid == 0) {
-        for (int st = 0; st < n_stages; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, NT / 32); }
+        for (int st = 0; st < MULTI_NS; ++st) { mbar_init(fullS + st, 1); ticket[st] = 0u; }
+        for (int q = 0; q < MULTI_MAXC * MULTI_MAXD; ++q) mbar_init(fullV + q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int64_t it = 0; it < my_tiles && it < n_stages; ++it) issue(it, (int)it);
+        for (int it = 0; it < my_tiles && it < MULTI_NS; ++it) issue_slab(it, it);
     }
+    for (int q = tid; q < NV * MULTI_ACC_LANES; q += MULTI_NT) sacc[q] = 0.0;
     __syncthreads();
 
-    int since = 0, st = 0;
-    uint32_t parity = 0;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-        while (!mbar_try_wait(full + st, parity)) {}
-        const float* buf = ring + (size_t)st * MULTI_STAGE_FLOATS;
-        const float* vbuf = buf + (2 + cc) * MULTI_TILE;
-        const int64_t i0 = tile_of(it) * MULTI_TILE;
-        F8 vout[MULTI_TILE / 256];
-        if (active) {
+    // lane 0 of a warp that has everything it needs from slab stage `st` in registers: the sixteenth warp to say so refills it
+    // (release / acquire on the ticket orders the sixteen warps' reads of the stage before the refill is issued; like the
+    // mbarrier hand-back of the single-contract ring, no proxy fence is needed for a read-then-bulk-write hand-over)
+    auto leave_stage = [&](int it, int st) {
+        unsigned int old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(ticket + st)) : "memory");
+        if ((old & (MULTI_MAXC - 1)) == MULTI_MAXC - 1 && it + MULTI_NS < my_tiles) issue_slab(it + MULTI_NS, st);
+    };
+    {
+        // per-warp constants: this contract's strike, coefficients and standardisation
+        SweepArgs w;  // the view fast2_compute / fast2_load_consts expect
+        memset(&w, 0, sizeof(w));
+        w.n = a.n; w.j = a.j; w.do_moments = a.do_moments; w.do_final = a.do_final; w.is_call = a.is_call; w.disc = a.disc;
+        w.K = a.K[cc];
+        w.d.coef = a.coef + (int64_t)cc * a.M * COEF_LD;
+        w.d.mu = const_cast<double*>(a.mu) + (int64_t)cc * a.M;
+        w.d.inv_s = const_cast<double*>(a.inv_s) + (int64_t)cc * a.M;
+        w.g = make_stepk(w.K, w.disc, w.is_call);  // per warp = per contract, once per launch
+        FastConsts<P> k;
+        fast2_load_consts<P>(w, k);
+        float2 la[NV];
+        int cnt = 0, since = 0;
 #pragma unroll
-            for (int g = 0; g < MULTI_TILE / 256; ++g) {  // 256 paths per warp iteration: lane -> 4 + 4 paths
-                const int oa = g * 256 + 4 * lane, ob = oa + 128;
-                const int64_t ia = i0 + oa, ib = i0 + ob;
-                F8 s8, p8;
-                F8& v8 = vout[g];
-                {
-                    const float4 x0 = *reinterpret_cast<const float4*>(buf + oa), x1 = *reinterpret_cast<const float4*>(buf + ob);
-                    s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
+        for (int m = 0; m < NV; ++m) la[m] = make_float2(0.f, 0.f);
+        if (active && want_v && lane == 0)
+            for (int it = 0; it < my_tiles && it < depth; ++it) issue_carry(it, it);
+
+        int st = 0, d = 0;
+        uint32_t parS = 0, parV = 0;
+        const bool common = mode == 0 && a.do_moments && !a.do_final;
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait(fullS + st, parS);
+            if (active) {
+                if (want_v) mbar_wait(fullV + c * MULTI_MAXD + d, parV);
+                const float* buf = slab + (size_t)st * (2 * MULTI_TILE);
+                const float* vbuf = carry + ((size_t)c * depth + d) * MULTI_TILE;
+                const int64_t i0 = tile_of(it) * MULTI_TILE;
+                // one tile = MULTI_TILE / 256 straight-line iterations of 256 paths (lane -> 4 + 4 paths); the common step
+                // (decision + moments, KIND 0) and whole tiles are compile-time cases, so nothing in the body branches
+                auto tile_body = [&](auto kind_tag, auto tail_tag) {
+                    constexpr int KIND = decltype(kind_tag)::value;
+                    constexpr bool TAIL = decltype(tail_tag)::value;
+                    const bool dm = KIND == 0 ? true : (a.do_moments != 0), wv = KIND == 0 ? true : want_v;
+#pragma unroll
+                    for (int h = 0; h < MULTI_TILE / 256; ++h) {
+                        const int oa = h * 256 + 4 * lane, ob = oa + 128;
+                        const int64_t ia = i0 + oa, ib = i0 + ob;
+                        F8 s8, p8, v8;
+                        {
+                            const float4 x0 = *reinterpret_cast<const float4*>(buf + oa), x1 = *reinterpret_cast<const float4*>(buf + ob);
+                            s8.q[0] = make_float2(x0.x, x0.y); s8.q[1] = make_float2(x0.z, x0.w); s8.q[2] = make_float2(x1.x, x1.y); s8.q[3] = make_float2(x1.z, x1.w);
+                        }
+                        p8 = s8; v8 = s8;
+                        if (dm) {
+                            const float4 x0 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + oa), x1 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + ob);
+                            p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
+                        }
+                        if (wv) {
+                            const float4 x0 = *reinterpret_cast<const float4*>(vbuf + oa), x1 = *reinterpret_cast<const float4*>(vbuf + ob);
+                            v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
+                        }
+                        if (h == MULTI_TILE / 256 - 1) {
+                            // the warp holds the rest of its tile in registers: hand the slab stage back and refill the own carry slot
+                            __syncwarp();
+                            if (lane == 0) {
+                                leave_stage(it, st);
+                                if (wv && it + depth < my_tiles) issue_carry(it + depth, d);
+                            }
+                        }
+                        fast2_compute<P, false, TAIL, KIND>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
+                        MCP_DBG_CHECK(ia >= 0 && (ia >= a.ld || ia + 4 <= a.ld) && (ib >= a.ld || ib + 4 <= a.ld), DBG_CARRY_STORE);
+                        if (!TAIL || ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
+                        if (!TAIL || ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
+                    }
+                };
+                const bool whole = i0 + MULTI_TILE <= a.n;
+                if (common) {
+                    if (whole) tile_body(std::integral_constant<int, 0>{}, std::false_type{});
+                    else tile_body(std::integral_constant<int, 0>{}, std::true_type{});
+                } else {
+                    if (whole) tile_body(std::integral_constant<int, 1>{}, std::false_type{});
+                    else tile_body(std::integral_constant<int, 1>{}, std::true_type{});
                 }
-                p8 = s8; v8 = s8;
-                if (a.do_moments) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + oa), x1 = *reinterpret_cast<const float4*>(buf + MULTI_TILE + ob);
-                    p8.q[0] = make_float2(x0.x, x0.y); p8.q[1] = make_float2(x0.z, x0.w); p8.q[2] = make_float2(x1.x, x1.y); p8.q[3] = make_float2(x1.z, x1.w);
-                }
-                if (mode != 2) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(vbuf + oa), x1 = *reinterpret_cast<const float4*>(vbuf + ob);
-                    v8.q[0] = make_float2(x0.x, x0.y); v8.q[1] = make_float2(x0.z, x0.w); v8.q[2] = make_float2(x1.x, x1.y); v8.q[3] = make_float2(x1.z, x1.w);
-                }
-                if (i0 + MULTI_TILE <= a.n) fast2_compute<P, false, false>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
-                else fast2_compute<P, false, true>(w, w.g, k, s8, p8, v8, ia, ib, mode, la, cnt);
-                MCP_DBG_CHECK(ia >= 0 && (ia >= a.ld || ia + 4 <= a.ld) && (ib >= a.ld || ib + 4 <= a.ld), DBG_CARRY_STORE);
-                if (ia < a.ld) stg4_stream(V + ia, v8.q[0], v8.q[1]);
-                if (ib < a.ld) stg4_stream(V + ib, v8.q[2], v8.q[3]);
-                if (++since == FLUSH) {
+                if (++since == FLUSH_TILES) {  // fp32 partials of <= 64 paths per lane, four lanes folded, then fp64
 #pragma unroll
                     for (int m = 0; m < NV; ++m) {
-                        sacc[m * NT + tid] += (double)(la[m].x + la[m].y);
+                        float v = la[m].x + la[m].y;
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if ((lane & 3) == 0) sacc[m * MULTI_ACC_LANES + c * 8 + (lane >> 2)] += (double)v;
                         la[m] = make_float2(0.f, 0.f);
                     }
                     since = 0;
                 }
+            } else if (lane == 0) {
+                leave_stage(it, st);  // an idle warp (fewer than 16 strikes) only keeps the slab ring turning
+            }
+            if (++st == MULTI_NS) { st = 0; parS ^= 1u; }
+            if (++d == depth) { d = 0; parV ^= 1u; }
+        }
+        if (a.do_moments || a.do_final) {
+            // per-contract (per-warp) partial row of this CTA, in a fixed lane order
+            double acc[NV];
+#pragma unroll
+            for (int m = 0; m < NV; ++m) acc[m] = ((lane & 3) == 0 ? sacc[m * MULTI_ACC_LANES + c * 8 + (lane >> 2)] : 0.0) + (double)(la[m].x + la[m].y);
+            acc[0] += (double)cnt;
+            double* prow = a.partial + ((int64_t)blockIdx.x * MULTI_MAXC + c) * MOM_LD;
+#pragma unroll
+            for (int m = 0; m < NV; ++m) {
+                const double sres = warp_sum(acc[m]);
+                if (lane == 0) prow[m] = sres;
             }
         }
-        // this warp is done with the stage (it read the tiles straight from shared memory); once all 16 warps have said so the
-        // slot is refilled -- no block-wide barrier, warps drift apart by up to the ring depth
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
-        if (tid == 0 && it + n_stages < my_tiles) {
-            while (!mbar_try_wait(empty + st, parity)) {}
-            issue(it + n_stages, st);
-        }
-        if (++st == n_stages) { st = 0; parity ^= 1u; }
     }
+#ifdef MCP_DEBUG_BOUNDS
+    __syncthreads();
+    if (tid < MCP_DBG_CANARY_BYTES / 4) MCP_DBG_CHECK(reinterpret_cast<unsigned int*>(after - MCP_DBG_CANARY_BYTES)[tid] == MCP_DBG_CANARY, DBG_RING_CANARY);
+#endif
     if (!(a.do_moments || a.do_final)) return;
-    // per-contract (per-warp) partial row of this CTA, in a fixed lane order
-    double acc[NV];
-#pragma unroll
-    for (int m = 0; m < NV; ++m) acc[m] = sacc[m * NT + tid] + (double)(la[m].x + la[m].y);
-    acc[0] += (double)cnt;
-    double* prow = a.partial + ((int64_t)blockIdx.x * MULTI_MAXC + c) * MOM_LD;
-#pragma unroll
-    for (int m = 0; m < NV; ++m) {
-        const double sres = warp_sum(acc[m]);
-        if (lane == 0) prow[m] = sres;
-    }
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
@@ -1761,11 +1840,12 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
     const int64_t ld = ps->ld;
     const int nv = 3 * p + 2 > 2 ? 3 * p + 2 : 2;
     MultiFn fn = pick_multi(p);
-    const size_t fixed = 128 + (size_t)nv * MULTI_MAXC * 32 * 8;
-    int n_stages = (int)((227u * 1024u - 12288u - fixed) / MULTI_STAGE_BYTES);
-    if (n_stages < 1) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm multi: shared memory");
-    const size_t smem = (size_t)n_stages * MULTI_STAGE_BYTES + fixed;
-    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, MULTI_MAXC * 32, smem, nullptr));
+    const size_t fixed = (size_t)MULTI_NS * MULTI_SLAB_STAGE_BYTES + MCP_DBG_CANARY_BYTES + MULTI_BAR_BYTES + (size_t)nv * MULTI_ACC_LANES * 8;
+    int depth = (int)((227u * 1024u - 12288u - fixed) / ((size_t)MULTI_MAXC * MULTI_CARRY_SLOT_BYTES));  // carry ring depth per contract warp
+    if (depth > MULTI_MAXD) depth = MULTI_MAXD;
+    if (depth < 2) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm multi: shared memory");
+    const size_t smem = fixed + (size_t)depth * MULTI_MAXC * MULTI_CARRY_SLOT_BYTES;
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, MULTI_NT, smem, nullptr));
     const int64_t ntile = (N + MULTI_TILE - 1) / MULTI_TILE;
     const int grid = (int)(ctx->sm_count < ntile ? ctx->sm_count : ntile);
     const int grid_aux = (int)((N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4) < (int64_t)ctx->sm_count * 3 ? (N + (int64_t)LSM_NT * 4 - 1) / ((int64_t)LSM_NT * 4)
@@ -1810,7 +1890,7 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
             a.terminal = (j == M - 1);
             a.do_moments = (j > 0 && kind[j - 1] == STEP_NORMAL);
             a.do_final = (j == 0);
-            fn<<<grid, MULTI_MAXC * 32, smem, st>>>(a, n_stages);
+            fn<<<grid, MULTI_NT, smem, st>>>(a, depth);
             MCP_LAUNCH_CHECK(ctx);
         }
         // per contract: mean known -> sum of squared deviations (two-pass standard error)

@@ -8,6 +8,9 @@
 // g, g + G, g + 2G, ... (mat_first / mat_stride) with its own un-sharded path set (pass a ctx WITHOUT a communicator;
 // with one attached, paths are sharded instead and every contract's regression is global).
 #include <math.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include <vector>
 
@@ -34,7 +37,11 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
     }
     mcp_pathset* ps = nullptr;
     if (n_steps_max >= 1) rc = mcp_pathset_create(ctx, n_paths, n_steps_max, MCP_F32, &ps);
-    for (int mi = mat_first; mi < n_maturities && rc == MCP_OK; mi += mat_stride) {
+    // longest maturity first: every grow-only workspace (scratch, carry) is sized once, by the first ladder
+    std::vector<int> owned;
+    for (int mi = mat_first; mi < n_maturities; mi += mat_stride) owned.push_back(mi);
+    for (size_t oi = owned.size(); oi-- > 0 && rc == MCP_OK;) {
+        const int mi = owned[oi];
         const double T = maturities[mi];
         const int n_steps = (int)floor(T * (double)steps_per_year);  // PredictionGen.cpp:718
         if (n_steps < 1) {  // PredictionGen.cpp:720-733 skips such rows and writes zeros
@@ -45,9 +52,12 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
             continue;
         }
         ps->n_steps = n_steps;  // a view of the first n_steps + 1 rows
+        const bool trace = getenv("MCP_SURFACE_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         cudaEventRecord(e0, ctx->stream);
         rc = mcp_gen_rbergomi(ctx, ps, model, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(mi + 1), path_offset, nullptr, nullptr);
         cudaEventRecord(e1, ctx->stream);
+        const auto t1 = std::chrono::steady_clock::now();
         if (rc == MCP_OK) {  // the whole strike ladder of this maturity: one sweep per 16 strikes in throughput mode
             mcp_lsm_params prm = *lsm_tmpl;
             prm.maturity = T;
@@ -63,6 +73,11 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
         if (rc == MCP_OK) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) gen_total += ms;
+            if (trace) {
+                const auto t2 = std::chrono::steady_clock::now();
+                fprintf(stderr, "surface: maturity %d (%d steps): generator call %.2f ms host (%.2f ms device), ladder call %.2f ms host\n", mi, n_steps,
+                        std::chrono::duration<double, std::milli>(t1 - t0).count(), ms, std::chrono::duration<double, std::milli>(t2 - t1).count());
+            }
         }
     }
     if (ps) {

@@ -89,7 +89,7 @@ def main():
     tag, launch_csv, reps = argv[0], argv[1], [a.split("=", 1) for a in argv[2:]]
     os.makedirs(out_dir, exist_ok=True)
     lines = [f"# ncu summary {tag}", ""]
-    if os.path.exists(launch_csv):
+    if os.path.exists(launch_csv) and os.path.getsize(launch_csv) > 0:
         agg = launches(launch_csv)
         total = sum(v[1] for v in agg.values())
         lines += [f"## launch list ({os.path.basename(launch_csv)}; cold-cache, serialised: compare SHARES)", "",
