@@ -21,8 +21,12 @@ struct RowDev {
     double K, r, dt, maturity, disc, sigma, dividend;
 };
 
+// 250 paths per row (PredictionGen.cpp:719) occupy 250 of a CTA's threads whatever its size, and the four pricers are chains of
+// short loops separated by block-wide sums: latency, not throughput.  256-thread CTAs, two per SM (ncu r02a: one 512-thread
+// CTA per SM issued 19 % of the time with 23 % of its stalls at barriers), let one row's barriers hide behind another's work.
+constexpr int ROWS_NT = 256;
 template <int P>
-__global__ void __launch_bounds__(SB_NT, 1) rows_price_kernel(const RowDev* __restrict__ rows, const float* __restrict__ slabs, int64_t ld, int n, int n_br,
+__global__ void __launch_bounds__(ROWS_NT, 2) rows_price_kernel(const RowDev* __restrict__ rows, const float* __restrict__ slabs, int64_t ld, int n, int n_br,
                                                              int max_iter, PhiloxKeys keys, uint64_t path_offset, double* __restrict__ out /*[rows][8]*/) {
     extern __shared__ double sm[];
     __shared__ double res[4];
@@ -107,7 +111,7 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
     const size_t smem = (4 * (size_t)n_paths + (size_t)(max_steps + 1) * 2 + 8) * sizeof(double);
     if (smem > 200 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: %d paths x %d steps does not fit one CTA", n_paths, max_steps);
     RowsFn fn = pick_rows(poly_order);
-    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, SB_NT, smem, nullptr));
+    MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, ROWS_NT, smem, nullptr));
     MCP_TRY(mcp_carry_reserve(ctx, (size_t)chunk * slab_stride * 4 + (size_t)chunk * (sizeof(RowDev) + 64) + 4096));
     float* d_slabs = (float*)ctx->carry;
     RowDev* d_rows = (RowDev*)((unsigned char*)ctx->carry + (size_t)chunk * slab_stride * 4);
@@ -142,7 +146,7 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
         if (rc != MCP_OK) break;
         cudaEventRecord(e1, ctx->stream);
         if (mcp_memcpy_async(ctx, d_rows, h_rows.data(), (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: H2D failed"); break; }
-        fn<<<nr, SB_NT, smem, ctx->stream>>>(d_rows, d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_out);
+        fn<<<nr, ROWS_NT, smem, ctx->stream>>>(d_rows, d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_out);
         ctx->launches++;
         cudaEventRecord(e2, ctx->stream);
         if (mcp_memcpy_async(ctx, h_out.data(), d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||

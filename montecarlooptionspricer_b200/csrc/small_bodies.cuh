@@ -6,7 +6,8 @@
 //   Branching    src/models/BranchingProcessPricer.cpp:41-134
 //   Asymptotic   src/models/AsymptoticAnalysisPricer.cpp:8-113
 //   Martingale   src/models/MartingaleOptimizationPricer.cpp:21-188
-// Every routine must be called by all SB_NT threads of the CTA.
+// Every routine must be called by ALL threads of the CTA (any block size that is a multiple of 32, at most SB_NT: the
+// loops stride by blockDim.x, so the batched row driver can run two 256-thread CTAs per SM where the per-row API uses 512).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,8 +38,7 @@ __device__ __forceinline__ void sb_sum(double (&acc)[NV], double* __restrict__ o
     __syncthreads();
     if (threadIdx.x < NV) {
         double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < SB_NT / 32; ++w) s += red[w][threadIdx.x];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
         out[threadIdx.x] = s;
     }
     __syncthreads();
@@ -69,12 +69,12 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
     __shared__ double mom[NV], cf[COEF_LD], sc[2];
     const int tid = threadIdx.x;
     // disc = exp(-r dt), evaluated by the caller on the host exactly like LSMPricer.cpp:46,69,92
-    for (int i = tid; i < n; i += SB_NT) sV[i] = payoff_fn(is_call, sb_ld<ST>(S + (int64_t)(M - 1) * ld + i), K);  // :37-40
+    for (int i = tid; i < n; i += (int)blockDim.x) sV[i] = payoff_fn(is_call, sb_ld<ST>(S + (int64_t)(M - 1) * ld + i), K);  // :37-40
     __syncthreads();
     for (int j = M - 2; j >= 0; --j) {                                                        // :42
         const ST* Sj = S + (int64_t)j * ld;
         if ((double)j * dt > maturity) {                                                      // :43-49
-            for (int i = tid; i < n; i += SB_NT) sV[i] *= disc;
+            for (int i = tid; i < n; i += (int)blockDim.x) sV[i] *= disc;
             if (tid == 0 && coef_out)
                 for (int k = 0; k < COEF_LD; ++k) coef_out[(int64_t)j * COEF_LD + k] = 0.0;
             __syncthreads();
@@ -84,7 +84,7 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
         double st[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) st[k] = 0.0;
-        for (int i = tid; i < n; i += SB_NT) {
+        for (int i = tid; i < n; i += (int)blockDim.x) {
             const double s = sb_ld<ST>(Sj + i);
             if (payoff_fn(is_call, s, K) > 1e-14) { st[0] += 1.0; st[1] += s; st[2] = fma(s, s, st[2]); }
         }
@@ -100,7 +100,7 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        for (int i = tid; i < n; i += SB_NT) {
+        for (int i = tid; i < n; i += (int)blockDim.x) {
             const double s = sb_ld<ST>(Sj + i);
             if (payoff_fn(is_call, s, K) > 1e-14) {
                 const double x = (s - mu) * inv_s, y = sV[i] * disc;                          // :69
@@ -126,7 +126,7 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
         double c[P + 1];
 #pragma unroll
         for (int k = 0; k <= P; ++k) c[k] = cf[k];
-        for (int i = tid; i < n; i += SB_NT) {
+        for (int i = tid; i < n; i += (int)blockDim.x) {
             const double s = sb_ld<ST>(Sj + i), pay = payoff_fn(is_call, s, K);
             const double x = (s - mu) * inv_s;
             double cont = c[P];
@@ -141,12 +141,12 @@ __device__ void sb_lsm(const ST* __restrict__ S, int64_t ld, int n, int M, doubl
     }
     // payoff averaging (:97-101) + two-pass standard error
     double t[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) t[0] += sV[i];
+    for (int i = tid; i < n; i += (int)blockDim.x) t[0] += sV[i];
     sb_sum<3>(t, mom);
     const double total = mom[0], mean = total / (double)n;
     __syncthreads();
     double q[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
         const double dlt = sV[i] - mean;
         q[0] = fma(dlt, dlt, q[0]);
         if (v_out) v_out[i] = sV[i];
@@ -168,7 +168,7 @@ __device__ void sb_branching(const ST* __restrict__ S, int64_t ld, int n, int j_
     __shared__ double red2[2];
     const int tid = threadIdx.x;
     double lo[2] = {0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
         F[i] = 0.0;
         best[i] = 0.0;
         double b = 0.0;  // lower bound: first listed date with a positive discounted payoff (:55-70)
@@ -185,7 +185,7 @@ __device__ void sb_branching(const ST* __restrict__ S, int64_t ld, int n, int j_
         const bool has_cont = j < ex_back, j_valid = j < kend;
         const double dj = exp(-r * ((double)j * dt));
         if (e) {
-            for (int i = tid; i < n; i += SB_NT) {
+            for (int i = tid; i < n; i += (int)blockDim.x) {
                 const double d = dj * payoff_fn(is_call, sb_ld<ST>(S + (int64_t)j * ld + i), K);
                 double cont = 0.0;
                 if (has_cont) {                                                               // :103
@@ -208,13 +208,13 @@ __device__ void sb_branching(const ST* __restrict__ S, int64_t ld, int n, int j_
             __syncthreads();  // every gather of date j is done before F takes index j in
         }
         if (j_valid)
-            for (int i = tid; i < n; i += SB_NT) {
+            for (int i = tid; i < n; i += (int)blockDim.x) {
                 const double d = dj * payoff_fn(is_call, sb_ld<ST>(S + (int64_t)j * ld + i), K);
                 if (d > F[i]) F[i] = d;
             }
         __syncthreads();
     }
-    for (int i = tid; i < n; i += SB_NT) lo[1] += best[i];
+    for (int i = tid; i < n; i += (int)blockDim.x) lo[1] += best[i];
     sb_sum<2>(lo, red2);
     if (tid < 2) out[tid] = red2[tid];
     __syncthreads();
@@ -230,7 +230,7 @@ __device__ void sb_asymptotic(const ST* __restrict__ S, int64_t ld, int n, int M
     int jend = M;
     for (int j = 0; j < M; ++j)
         if ((double)j * dt > maturity) { jend = j; break; }                                   // :71
-    for (int j = tid; j < M; j += SB_NT) {
+    for (int j = tid; j < M; j += (int)blockDim.x) {
         const double t = (double)j * dt, eps = maturity - t;
         double b = K;
         if (!(eps < 1e-10)) {                                                                 // :10-11, :25-26
@@ -243,7 +243,7 @@ __device__ void sb_asymptotic(const ST* __restrict__ S, int64_t ld, int n, int M
     }
     __syncthreads();
     double acc[2] = {0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
         double best = 0.0;
         for (int j = 0; j < jend; ++j) {
             const double s = sb_ld<ST>(S + (int64_t)j * ld + i);
@@ -277,14 +277,14 @@ __device__ void sb_martingale(const ST* __restrict__ S, int64_t ld, int n, int M
     int jend = M;
     for (int j = 0; j < M; ++j)
         if ((double)j * dt > maturity) { jend = j; break; }
-    for (int j = tid; j < M; j += SB_NT) {                                                    // PathDiscountFactor (.h:44-49)
+    for (int j = tid; j < M; j += (int)blockDim.x) {                                                    // PathDiscountFactor (.h:44-49)
         double t = (double)j * dt;
         if (t > maturity) t = maturity;
         DF[j] = exp(-r * t);
     }
     __syncthreads();
     double pr[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) {                                                    // :72-94, :130-150
+    for (int i = tid; i < n; i += (int)blockDim.x) {                                                    // :72-94, :130-150
         double best = 0.0, s_stop = sb_ld<ST>(S + i);
         int idx = 0;
         for (int j = 0; j < jend; ++j) {
@@ -312,7 +312,7 @@ __device__ void sb_martingale(const ST* __restrict__ S, int64_t ld, int n, int M
     }
     // standardisation over all 2n samples, then the normal-equation moments (:152-166)
     double sq[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) sq[0] += smp[i] * smp[i] + smp[2 * n + i] * smp[2 * n + i];
+    for (int i = tid; i < n; i += (int)blockDim.x) sq[0] += smp[i] * smp[i] + smp[2 * n + i] * smp[2 * n + i];
     sb_sum<3>(sq, sc);
     double mu, inv_s;
     sb_scale(cnt, s1, sc[0], K, &mu, &inv_s);
@@ -320,7 +320,7 @@ __device__ void sb_martingale(const ST* __restrict__ S, int64_t ld, int n, int M
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    for (int i = tid; i < n; i += SB_NT) {
+    for (int i = tid; i < n; i += (int)blockDim.x) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double x = (smp[(2 * h) * n + i] - mu) * inv_s, y = smp[(2 * h + 1) * n + i];
@@ -350,12 +350,12 @@ __device__ void sb_martingale(const ST* __restrict__ S, int64_t ld, int n, int M
         return v;
     };
     double of[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) of[0] += poly(sb_ld<ST>(S + i));                     // :172-177
+    for (int i = tid; i < n; i += (int)blockDim.x) of[0] += poly(sb_ld<ST>(S + i));                     // :172-177
     sb_sum<3>(of, sc);
     const double offset = sc[0] / (double)n;
     __syncthreads();
     double du[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += SB_NT) {                                                    // :96-117
+    for (int i = tid; i < n; i += (int)blockDim.x) {                                                    // :96-117
         double best = 0.0;
         for (int j = 0; j < jend; ++j) {
             const double s = sb_ld<ST>(S + (int64_t)j * ld + i);
