@@ -174,6 +174,17 @@ int mcp_lsm_price(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *p, 
 int mcp_lsm_price_multi(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *prm, const double *strikes, int n_strikes,
                         mcp_lsm_result *res);
 
+/* [new -- the reference computes no error estimate] Out-of-sample value of a fitted exercise policy.  coeffs_std: host
+ * [n_steps][poly_order+3], the MCP_BASIS_STANDARDISED table returned by mcp_lsm_price on ANOTHER, independent path set with the
+ * same contract and step grid.  Every path of `ps` is stopped at the first date where the reference's own rule exercises
+ * (in the money by more than 1e-14 and !(immediate < fitted continuation), LSMPricer.cpp:55,85; the last column always pays
+ * off, :37-40; no exercise past maturity, :43-49); res->price is the mean discounted realised payoff, res->std_error its
+ * standard error (paths are independent given the coefficients, so this one is exact, unlike mcp_lsm_result::std_error of
+ * the in-sample run), and in expectation a LOWER bound of the true price.  mean_stop_index (nullable): average stopping
+ * column.  With a communicator attached the sums run over all ranks' shards. */
+int mcp_lsm_policy_value(mcp_ctx *ctx, const mcp_pathset *ps, const mcp_lsm_params *prm, const double *coeffs_std,
+                         mcp_lsm_result *res, double *mean_stop_index);
+
 /* One call = LSM::PredictOptionPrice(pricePaths, r, strike, maturity, dt, isCall, polyOrder): uploads
  * n_paths host rows of n_cols doubles (kept in fp64 on the device), prices, returns the mean. */
 int mcp_lsm_price_host_rows(mcp_ctx *ctx, const double *const *rows, int64_t n_paths, int n_cols, double r,

@@ -92,6 +92,7 @@ SIGNATURES = {
                                  C.POINTER(C.c_uint32)]),
     "mcp_lsm_price": (C.c_int, [_vp, _vp, C.POINTER(LsmParams), C.POINTER(LsmResult), _dp, _ip, _dp]),
     "mcp_lsm_price_multi": (C.c_int, [_vp, _vp, C.POINTER(LsmParams), _dp, C.c_int, C.POINTER(LsmResult)]),
+    "mcp_lsm_policy_value": (C.c_int, [_vp, _vp, C.POINTER(LsmParams), _dp, C.POINTER(LsmResult), _dp]),
     "mcp_lsm_price_host_rows": (C.c_int, [_vp, C.POINTER(_dp), C.c_int64, C.c_int, C.c_double, C.c_double,
                                           C.c_double, C.c_double, C.c_int, C.c_int, _dp]),
     "mcp_price_rbergomi_lsm": (C.c_int, [_vp, C.POINTER(RbergomiParams), C.POINTER(LsmParams), C.c_int64, C.c_int,

@@ -1926,6 +1926,111 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
     return MCP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Out-of-sample value of a fitted exercise policy [new: the reference has no error estimate at all].
+// LSM::PredictOptionPrice carries FITTED continuation values backwards (LSMPricer.cpp:78-86), so the spread of V[:,0] says
+// nothing about the noise of the regressions: measured seed-to-seed scatter is 2-4x mcp_lsm_result::std_error.
+// The honest companion number: take the coefficient tables of one run (MCP_BASIS_STANDARDISED rows), generate an INDEPENDENT
+// path set, stop every path at the first date where the same rule the reference applies says "exercise"
+// (in the money by > 1e-14 and !(immediate < fitted continuation), :55,:85; the last column always pays off, :37-40; dates
+// past maturity cannot be exercised, :43-49) and average the discounted realised payoffs.  Paths are independent given the
+// coefficients, so sqrt(var / N) IS the standard error of this mean; as the value of a feasible stopping rule it is a lower
+// bound of the true price in expectation, where the in-sample value-iteration number is biased high.
+// One streaming pass, thread per path, 4 B per path-step until the path has stopped.
+// ---------------------------------------------------------------------------------------------------------
+template <typename ST>
+__global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict__ S, int64_t ld, int64_t n, int M, int p, const double* __restrict__ tab /*[M][COEF_LD + 2]*/,
+                                                          const int* __restrict__ kind, double K, int is_call, double disc, double* __restrict__ partial) {
+    double acc[3] = {0.0, 0.0, 0.0};  // sum of discounted payoffs, sum of squares, sum of stopping indices
+    for (int64_t i = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LSM_NT) {
+        double df = 1.0, val = 0.0;
+        int tau = M - 1;
+        for (int j = 0; j < M; ++j, df *= disc) {
+            const double s = (double)S[(int64_t)j * ld + i];
+            const double pay = payoff_fn(is_call, s, K);
+            if (j == M - 1) { val = df * pay; break; }
+            if (__ldg(kind + j) != STEP_NORMAL || !(pay > 1e-14)) continue;
+            const double* c = tab + (size_t)j * (COEF_LD + 2);
+            const double x = (s - __ldg(c + COEF_LD)) * __ldg(c + COEF_LD + 1);
+            double cont = __ldg(c + p);
+            for (int k = p - 1; k >= 0; --k) cont = fma(cont, x, __ldg(c + k));
+            if (!(pay < cont)) { val = df * pay; tau = j; break; }
+        }
+        acc[0] += val;
+        acc[1] = fma(val, val, acc[1]);
+        acc[2] += (double)tau;
+    }
+    block_reduce_to_partial<3>(acc, partial + (int64_t)blockIdx.x * MOM_LD);
+}
+
+extern "C" int mcp_lsm_policy_value(mcp_ctx* ctx, const mcp_pathset* ps, const mcp_lsm_params* prm, const double* coeffs_std, mcp_lsm_result* res,
+                                    double* mean_stop_index) {
+    if (!ctx || !prm || !coeffs_std || !res) return MCP_ERR_INVALID;
+    if (!ps || ps->n_paths <= 0) return mcp_fail(ctx, MCP_ERR_EMPTY_PATHS, "LSM::PredictOptionPrice: Empty pricePaths.");
+    if (ps->ctx != ctx) return mcp_fail(ctx, MCP_ERR_INVALID, "lsm: pathset belongs to another ctx");
+    const int p = prm->poly_order;
+    if (p < 0 || p > MAXP) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "lsm: poly_order %d outside [0, %d]", p, MAXP);
+    MCP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int M = ps->n_steps + 1;
+    const int64_t N = ps->n_paths;
+    int64_t grid = (N + LSM_NT - 1) / LSM_NT;
+    if (grid > (int64_t)ctx->sm_count * 8) grid = (int64_t)ctx->sm_count * 8;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_tab = take((size_t)M * (COEF_LD + 2) * 8), o_kind = take((size_t)M * 4), o_part = take((size_t)grid * MOM_LD * 8), o_fin = take(4 * 8);
+    MCP_TRY(mcp_scratch_reserve(ctx, off));
+    unsigned char* sb = (unsigned char*)ctx->scratch;
+    std::vector<double> tab((size_t)M * (COEF_LD + 2), 0.0);
+    for (int j = 0; j + 1 < M; ++j) {  // caller's rows: [c_0 .. c_p, mu, 1/s]
+        const double* row = coeffs_std + (size_t)j * (p + 3);
+        for (int k = 0; k <= p; ++k) tab[(size_t)j * (COEF_LD + 2) + k] = row[k];
+        tab[(size_t)j * (COEF_LD + 2) + COEF_LD] = row[p + 1];
+        tab[(size_t)j * (COEF_LD + 2) + COEF_LD + 1] = row[p + 2];
+    }
+    std::vector<int> kind(M, STEP_NORMAL);
+    for (int j = 0; j < M; ++j) kind[j] = ((double)j * prm->dt > prm->maturity) ? STEP_DISCOUNT : STEP_NORMAL;  // LSMPricer.cpp:43-44
+    cudaStream_t st = ctx->stream;
+    const uint64_t launches0 = ctx->launches;
+    MCP_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    MCP_TRY(mcp_h2d(ctx, sb + o_tab, tab.data(), tab.size() * 8));
+    MCP_TRY(mcp_h2d(ctx, sb + o_kind, kind.data(), (size_t)M * 4));
+    const double disc = exp(-prm->r * prm->dt);
+    double* d_part = (double*)(sb + o_part);
+    double* d_fin = (double*)(sb + o_fin);
+    if (ps->dtype == MCP_F32)
+        lsm_policy_kernel<float><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)ps->data, ps->ld, N, M, p, (const double*)(sb + o_tab), (const int*)(sb + o_kind),
+                                                                      prm->strike, prm->is_call, disc, d_part);
+    else
+        lsm_policy_kernel<double><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)ps->data, ps->ld, N, M, p, (const double*)(sb + o_tab), (const int*)(sb + o_kind),
+                                                                       prm->strike, prm->is_call, disc, d_part);
+    MCP_LAUNCH_CHECK(ctx);
+    lsm_reduce_kernel<<<1, 256, 0, st>>>(d_part, (int)grid, 3, d_fin);
+    MCP_LAUNCH_CHECK(ctx);
+    const double nloc = (double)N;
+    MCP_TRY(mcp_h2d(ctx, d_fin + 3, &nloc, 8));
+    MCP_TRY(mcp_allreduce_f64(ctx, d_fin, 4));  // path-sharded ranks: global sums (no-op without a communicator)
+    MCP_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    double fin[4] = {0, 0, 0, 0};
+    double* fp = (double*)mcp_stage_alloc(ctx, sizeof(fin));
+    MCP_CUDA(ctx, mcp_memcpy_async(ctx, fp ? fp : fin, d_fin, sizeof(fin), cudaMemcpyDeviceToHost, st));
+    MCP_CUDA(ctx, cudaStreamSynchronize(st));
+    MCP_CUDA(ctx, cudaGetLastError());
+    if (fp) memcpy(fin, fp, sizeof(fin));
+    const double ng = fin[3], mean = fin[0] / ng;
+    res->price = mean;
+    res->sum_v0 = fin[0];
+    res->sum_sq_dev = fin[1] - ng * mean * mean;  // one pass: sum of squares minus N mean^2 (payoffs are O(K), N mean^2 / sum sq ~ 1e-1: no cancellation trouble in fp64)
+    if (res->sum_sq_dev < 0.0) res->sum_sq_dev = 0.0;
+    res->n_paths_global = (int64_t)llround(ng);
+    res->std_error = ng > 1.0 ? sqrt(res->sum_sq_dev / (ng - 1.0) / ng) : 0.0;
+    float ms = 0.f;
+    MCP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->elapsed_ms = ms;
+    res->n_kernel_launches = (int)(ctx->launches - launches0);
+    if (mean_stop_index) *mean_stop_index = fin[2] / ng;
+    return MCP_OK;
+}
+
 extern "C" int mcp_lsm_price_host_rows(mcp_ctx* ctx, const double* const* rows, int64_t n_paths, int n_cols, double r, double strike,
                                        double maturity, double dt, int is_call, int poly_order, double* price) {
     if (!ctx || !price) return MCP_ERR_INVALID;

@@ -208,6 +208,18 @@ class Engine:
         return LsmOutput(res.price, res.std_error, res.sum_v0, res.sum_sq_dev, res.n_paths_global, res.elapsed_ms,
                          res.n_kernel_launches, co, fe, v0)
 
+    def lsm_policy_value(self, ps: "PathSet", coeffs_std: np.ndarray, r, strike, maturity, dt, is_call, poly_order):
+        """Out-of-sample value of a fitted exercise policy (mcp_lsm_policy_value): `coeffs_std` is the MCP_BASIS_STANDARDISED
+        table of lsm_price(..., want_coeffs=True) on an INDEPENDENT path set.  Returns (LsmOutput, mean stopping column)."""
+        co = np.ascontiguousarray(coeffs_std, dtype=np.float64)
+        if co.shape != (max(ps.n_steps, 1), poly_order + 3):
+            raise ValueError(f"coeffs_std must be [{ps.n_steps}][{poly_order + 3}] (MCP_BASIS_STANDARDISED rows)")
+        prm = LsmParams(r, strike, maturity, dt, int(bool(is_call)), poly_order, capi.MCP_BASIS_STANDARDISED, capi.MCP_F64)
+        res, stop = LsmResult(), C.c_double()
+        self._chk(self._L.mcp_lsm_policy_value(self._h, ps._h, C.byref(prm), co.ctypes.data_as(capi._dp), C.byref(res), C.byref(stop)))
+        return (LsmOutput(res.price, res.std_error, res.sum_v0, res.sum_sq_dev, res.n_paths_global, res.elapsed_ms, res.n_kernel_launches),
+                stop.value)
+
     def lsm_price_multi(self, ps: "PathSet", strikes, r, maturity, dt, is_call, poly_order, carry: int = capi.MCP_F32):
         """Several strikes on the same path set (one sweep for the whole ladder in throughput mode)."""
         ks = np.ascontiguousarray(strikes, dtype=np.float64)
