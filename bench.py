@@ -19,6 +19,8 @@ backward induction (fp64 moments) -> price + standard error.  Prints ONE JSON li
   parity_mode  the bit-exact (fp64 carry, fp64 decisions) sweep timed on the same slab, against its 20 B/path-step
   shard_parity (N > 1) a 2^20-path fp64-carry problem priced sharded and unsharded: relative price difference and
                first-exercise mismatches -- measured in this run, outside the timed regions
+  policy_value what the fitted exercise rule earns on an independent path set (lower bound, exact standard error) next to the
+               in-sample value-iteration price the reference's estimator reports
   configs      the other BASELINE configs (1, 2, 4, 5) and the reference's row workload, one number each
   cpu_baseline the reference's unmodified generator + LSM (oracle/_ref) on a bounded sample, all host cores, every N
 """
@@ -419,6 +421,20 @@ def main():
                        "frac_hbm": 20.0 * n_loc * (N_STEPS + 1) / (lsm64_ms * 1e-3) / 1e9 / peaks()[0],
                        "price": o64.price, "rel_diff_to_fp32_carry_price": abs(o64.price - price) / o64.price}
 
+    # ---- what the fitted policy earns on fresh paths (mcp_lsm_policy_value; outside the timed regions) ----
+    policy = None
+    try:
+        fit = eng.lsm_price(ps, MODEL["r"], STRIKE, MATURITY, MODEL["dt"], False, POLY, basis=m.MCP_BASIS_STANDARDISED,
+                            carry=m.MCP_F32 if args.carry == "f32" else m.MCP_F64, want_coeffs=True)
+        eng.gen_rbergomi(ps, MODEL["S0"], MODEL["r"], MODEL["xi"], MODEL["H"], MODEL["eta"], MODEL["rho"], MODEL["dt"], seed=4242, path_offset=path_offset)
+        oos, stop = eng.lsm_policy_value(ps, fit.coeffs, MODEL["r"], STRIKE, MATURITY, MODEL["dt"], False, POLY)
+        policy = {"what": "mean discounted payoff of the fitted exercise rule on an INDEPENDENT path set of the same size: a lower bound in expectation, "
+                          "with an exact standard error (the in-sample `price` carries fitted values and is biased high; its std_error ignores regression noise)",
+                  "in_sample_price": fit.price, "in_sample_std_error": fit.std_error, "policy_value": oos.price, "policy_value_std_error": oos.std_error,
+                  "mean_stopping_step": stop, "pass_ms": oos.elapsed_ms}
+    except Exception as e:  # never let a reporting extra take the bench line down
+        policy = {"error": str(e)[:200]}
+
     # ---- timed region B: end to end through the public host call (host structs in, host result out) ----
     ps.close()  # the host call owns (and caches) its own slab
     for w in range(2):
@@ -552,6 +568,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "parity_mode": parity_mode,
+        "policy_value": policy,
             "shard_parity": shard_parity,
             "configs": configs,
             "cpu_baseline": cpu,
