@@ -89,6 +89,8 @@ struct mcp_ctx {
     size_t slab_pool_bytes = 0;
     // cached pathset for mcp_price_rbergomi_lsm
     mcp_pathset* cached_ps = nullptr;
+    // cached slab of mcp_price_surface_rbergomi_lsm (a 4 GB cudaMalloc / cudaFree pair per call costs more than the generation)
+    mcp_pathset* cached_surface_ps = nullptr;
     // every pathset created on this ctx and not destroyed yet: mcp_destroy releases what the caller forgot
     std::vector<mcp_pathset*> live_ps;
     // optional per-kernel timing

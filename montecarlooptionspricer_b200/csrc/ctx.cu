@@ -234,6 +234,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->cached_ps) mcp_pathset_destroy(ctx->cached_ps);
+    if (ctx->cached_surface_ps) mcp_pathset_destroy(ctx->cached_surface_ps);
     while (!ctx->live_ps.empty()) mcp_pathset_destroy(ctx->live_ps.back());  // handles the caller never destroyed (they are dead after this)
     for (auto& blk : ctx->slab_pool) cudaFree(blk.first);
     ctx->slab_pool.clear();

@@ -1941,24 +1941,56 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
 template <typename ST>
 __global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict__ S, int64_t ld, int64_t n, int M, int p, const double* __restrict__ tab /*[M][COEF_LD + 2]*/,
                                                           const int* __restrict__ kind, double K, int is_call, double disc, double* __restrict__ partial) {
+    // A CTA owns tiles of POL_PPT * LSM_NT consecutive paths and walks DOWN the rows with them (row j of the whole tile, then row
+    // j + 1): every thread has POL_PPT independent loads in flight and a row's 8 KB come from one page -- a thread that walks one
+    // path through 253 rows that lie 268 MB apart spends its time in TLB misses (measured: 82 ms instead of 22 at 2^26 paths).
+    constexpr int POL_PPT = 8;
     double acc[3] = {0.0, 0.0, 0.0};  // sum of discounted payoffs, sum of squares, sum of stopping indices
-    for (int64_t i = (int64_t)blockIdx.x * LSM_NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * LSM_NT) {
-        double df = 1.0, val = 0.0;
-        int tau = M - 1;
-        for (int j = 0; j < M; ++j, df *= disc) {
-            const double s = (double)S[(int64_t)j * ld + i];
-            const double pay = payoff_fn(is_call, s, K);
-            if (j == M - 1) { val = df * pay; break; }
-            if (__ldg(kind + j) != STEP_NORMAL || !(pay > 1e-14)) continue;
-            const double* c = tab + (size_t)j * (COEF_LD + 2);
-            const double x = (s - __ldg(c + COEF_LD)) * __ldg(c + COEF_LD + 1);
-            double cont = __ldg(c + p);
-            for (int k = p - 1; k >= 0; --k) cont = fma(cont, x, __ldg(c + k));
-            if (!(pay < cont)) { val = df * pay; tau = j; break; }
+    const int64_t tile_paths = (int64_t)POL_PPT * LSM_NT;
+    for (int64_t t0 = (int64_t)blockIdx.x * tile_paths; t0 < n; t0 += (int64_t)gridDim.x * tile_paths) {
+        double val[POL_PPT];
+        int tau[POL_PPT];
+        unsigned alive = 0;
+#pragma unroll
+        for (int q = 0; q < POL_PPT; ++q) {
+            val[q] = 0.0;
+            tau[q] = M - 1;
+            if (t0 + q * LSM_NT + threadIdx.x < n) alive |= 1u << q;
         }
-        acc[0] += val;
-        acc[1] = fma(val, val, acc[1]);
-        acc[2] += (double)tau;
+        const unsigned mine = alive;
+        double df = 1.0;
+        for (int j = 0; j < M; ++j, df *= disc) {
+            if (__syncthreads_and(alive == 0u)) break;  // the whole tile has stopped
+            const ST* row = S + (int64_t)j * ld + t0 + threadIdx.x;
+            ST buf[POL_PPT];
+#pragma unroll
+            for (int q = 0; q < POL_PPT; ++q) buf[q] = (alive >> q) & 1u ? row[q * LSM_NT] : (ST)0;
+            const bool last = j == M - 1, normal = __ldg(kind + j) == STEP_NORMAL;
+            if (!last && !normal) continue;
+            const double* c = tab + (size_t)j * (COEF_LD + 2);
+            const double mu = __ldg(c + COEF_LD), is = __ldg(c + COEF_LD + 1);
+#pragma unroll
+            for (int q = 0; q < POL_PPT; ++q) {
+                if (!((alive >> q) & 1u)) continue;
+                const double s = (double)buf[q];
+                const double pay = payoff_fn(is_call, s, K);
+                bool stop = last;
+                if (!last && pay > 1e-14) {
+                    const double x = (s - mu) * is;
+                    double cont = __ldg(c + p);
+                    for (int k = p - 1; k >= 0; --k) cont = fma(cont, x, __ldg(c + k));
+                    stop = !(pay < cont);
+                }
+                if (stop) { val[q] = df * pay; tau[q] = j; alive &= ~(1u << q); }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < POL_PPT; ++q)
+            if ((mine >> q) & 1u) {
+                acc[0] += val[q];
+                acc[1] = fma(val[q], val[q], acc[1]);
+                acc[2] += (double)tau[q];
+            }
     }
     block_reduce_to_partial<3>(acc, partial + (int64_t)blockIdx.x * MOM_LD);
 }
@@ -1973,7 +2005,7 @@ extern "C" int mcp_lsm_policy_value(mcp_ctx* ctx, const mcp_pathset* ps, const m
     MCP_CUDA(ctx, cudaSetDevice(ctx->device));
     const int M = ps->n_steps + 1;
     const int64_t N = ps->n_paths;
-    int64_t grid = (N + LSM_NT - 1) / LSM_NT;
+    int64_t grid = (N + (int64_t)8 * LSM_NT - 1) / ((int64_t)8 * LSM_NT);  // POL_PPT paths per thread
     if (grid > (int64_t)ctx->sm_count * 8) grid = (int64_t)ctx->sm_count * 8;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };

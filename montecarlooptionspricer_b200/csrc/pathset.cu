@@ -67,6 +67,7 @@ int mcp_pathset_destroy(mcp_pathset* ps) {
         if (ctx->live_ps[i] == ps) { ctx->live_ps.erase(ctx->live_ps.begin() + (long)i); break; }
     if (ps->capacity > ((size_t)256 << 20)) cudaStreamSynchronize(ctx->stream);  // pooled blocks are reused in stream order instead
     if (ctx->cached_ps == ps) ctx->cached_ps = nullptr;
+    if (ctx->cached_surface_ps == ps) ctx->cached_surface_ps = nullptr;
     constexpr size_t POOL_BLOCK_MAX = (size_t)256 << 20, POOL_TOTAL_MAX = (size_t)1 << 30;
     if (ps->data && ps->capacity <= POOL_BLOCK_MAX && ctx->slab_pool_bytes + ps->capacity <= POOL_TOTAL_MAX && ctx->slab_pool.size() < 16) {
         ctx->slab_pool.push_back(std::make_pair(ps->data, ps->capacity));

@@ -35,8 +35,18 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
         const int n_steps = (int)floor(maturities[mi] * (double)steps_per_year);
         if (n_steps > n_steps_max) n_steps_max = n_steps;
     }
-    mcp_pathset* ps = nullptr;
-    if (n_steps_max >= 1) rc = mcp_pathset_create(ctx, n_paths, n_steps_max, MCP_F32, &ps);
+    // ... and the slab survives the call: the next surface with the same path count and no more rows reuses it
+    mcp_pathset* ps = ctx->cached_surface_ps;
+    int n_rows_have = ps ? ps->n_steps : 0;
+    if (ps && (ps->n_paths != n_paths || ps->dtype != MCP_F32 || n_rows_have < n_steps_max)) {
+        mcp_pathset_destroy(ps);
+        ps = nullptr;
+    }
+    if (!ps && n_steps_max >= 1) {
+        rc = mcp_pathset_create(ctx, n_paths, n_steps_max, MCP_F32, &ps);
+        n_rows_have = n_steps_max;
+        if (rc == MCP_OK) ctx->cached_surface_ps = ps;
+    }
     // longest maturity first: every grow-only workspace (scratch, carry) is sized once, by the first ladder
     std::vector<int> owned;
     for (int mi = mat_first; mi < n_maturities; mi += mat_stride) owned.push_back(mi);
@@ -80,10 +90,7 @@ extern "C" int mcp_price_surface_rbergomi_lsm(mcp_ctx* ctx, const mcp_rbergomi_p
             }
         }
     }
-    if (ps) {
-        ps->n_steps = n_steps_max;
-        mcp_pathset_destroy(ps);
-    }
+    if (ps) ps->n_steps = n_rows_have;  // the cached slab keeps its full height
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (gen_ms_total) *gen_ms_total = gen_total;

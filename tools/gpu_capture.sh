@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 timeout 300 $NCU -k regex:n256pair -c 1 -o $out/prof_gen python tools/one_price.py 26 1 > $out/ncu_gen.log 2>&1
 timeout 300 $NCU -k regex:lsm_sweep_tma_kernel -s 100 -c 1 -o $out/prof_sweep python tools/one_price.py 26 1 > $out/ncu_sweep.log 2>&1
 timeout 300 $NCU -k regex:lsm_sweep_tma64 -s 100 -c 1 -o $out/prof_sweep64 python tools/one_lsm.py 26 f64 > $out/ncu_sweep64.log 2>&1
-timeout 300 $NCU -k regex:lsm_multi_kernel -s 100 -c 1 -o $out/prof_multi python tools/one_surface.py 1 22 > $out/ncu_multi.log 2>&1
+timeout 300 $NCU -k regex:lsm_multi_kernel -s 300 -c 1 -o $out/prof_multi python tools/one_surface.py 1 22 > $out/ncu_multi.log 2>&1
 timeout 300 $NCU -k 'regex:rbergomi_rows_kernel|rows_price_kernel' -s 2 -c 2 -o $out/prof_rows python tools/rows_throughput.py 4096 > $out/ncu_rows.log 2>&1
 timeout 300 $NCU -k 'regex:dual_nested_kernel|gbm_paths_kernel' -c 3 -o $out/prof_dual python tools/dual_bench.py 16 1000 > $out/ncu_dual.log 2>&1
 MCP_SWEEP_IMPL=4 timeout 300 $NCU -k regex:lsm_persist -c 1 -o $out/prof_persist python tools/one_lsm.py 23 f32 > $out/ncu_persist.log 2>&1
