@@ -261,7 +261,7 @@ def other_configs(m, eng, eng_solo, rank, world, tmax, barrier, peak):
         out["cfg5"] = {"workload": "256 contracts = 16 strikes x 16 maturities, 2^22 paths each, rBergomi LSM p=3, maturities split over ranks (no collective)",
                        "time_s": t5, "gen_ms_rank0": gms, "lsm_ms_rank0": lms, "atm_1y_put": float(px[-1, 8]) if not np.isnan(px[-1, 8]) else None,
                        "lsm_multi_kernel_frac_hbm_rank0": (cps * bytes_cps / (lms * 1e-3) / 1e9 / peak) if lms > 0 else None,
-                       "lsm_multi_bytes_per_contract_path_step": bytes_cps}
+                       "lsm_multi_bytes_per_contract_path_step": bytes_cps, "ncu": ncu_constants().get("strike_ladder")}
         # spot check: the ATM strike of the first maturity this rank owns, priced alone through mcp_price_rbergomi_lsm-shaped calls
         ps = eng_solo.pathset(1 << 22, steps5[0])
         eng_solo.gen_rbergomi(ps, MODEL["S0"], MODEL["r"], MODEL["xi"], MODEL["H"], MODEL["eta"], MODEL["rho"], MODEL["dt"],
@@ -419,7 +419,8 @@ def main():
         parity_mode = {"what": "fp64 carry, every decision in fp64 on the stored values (exercise indices bit-exact with the oracle)",
                        "lsm_ms": lsm64_ms, "us_per_sweep_step": 1e3 * lsm64_ms / (N_STEPS + 1), "algorithmic_bytes_per_path_step": 20.0,
                        "frac_hbm": 20.0 * n_loc * (N_STEPS + 1) / (lsm64_ms * 1e-3) / 1e9 / peaks()[0],
-                       "price": o64.price, "rel_diff_to_fp32_carry_price": abs(o64.price - price) / o64.price}
+                       "price": o64.price, "rel_diff_to_fp32_carry_price": abs(o64.price - price) / o64.price,
+                       "ncu": (ncu_constants().get("sweep_parity") if world == 1 else None)}
 
     # ---- what the fitted policy earns on fresh paths (mcp_lsm_policy_value; outside the timed regions) ----
     policy = None
