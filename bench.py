@@ -210,7 +210,7 @@ def other_configs(m, eng, eng_solo, rank, world, tmax, barrier, peak):
         z = rng.standard_normal((N, n)).astype(np.float32).astype(np.float64)
         dt = 1.0 / n
         paths = 100.0 * np.exp(np.cumsum(np.concatenate([np.zeros((N, 1)), (0.05 - 0.02) * dt + 0.2 * np.sqrt(dt) * z], axis=1), axis=1))
-        eng_solo.lsm_price_host_rows(paths[:4096], 0.05, 100.0, 1.0, dt, False, 3)  # warm-up
+        eng_solo.lsm_price_host_rows(paths, 0.05, 100.0, 1.0, dt, False, 3)  # warm-up at full size: pinned staging, scratch and slab pool are sized once
         h0, d0 = eng_solo.copy_counters()
         t0 = time.perf_counter()
         px = eng_solo.lsm_price_host_rows(paths, 0.05, 100.0, 1.0, dt, False, 3)
