@@ -1938,12 +1938,12 @@ extern "C" int mcp_lsm_price_multi(mcp_ctx* ctx, const mcp_pathset* ps, const mc
 // bound of the true price in expectation, where the in-sample value-iteration number is biased high.
 // One streaming pass, thread per path, 4 B per path-step until the path has stopped.
 // ---------------------------------------------------------------------------------------------------------
-template <typename ST>
-__global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict__ S, int64_t ld, int64_t n, int M, int p, const double* __restrict__ tab /*[M][COEF_LD + 2]*/,
+template <typename ST, int P>
+__global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict__ S, int64_t ld, int64_t n, int M, const double* __restrict__ tab /*[M][COEF_LD + 2]*/,
                                                           const int* __restrict__ kind, double K, int is_call, double disc, double* __restrict__ partial) {
     // A CTA owns tiles of POL_PPT * LSM_NT consecutive paths and walks DOWN the rows with them (row j of the whole tile, then row
     // j + 1): every thread has POL_PPT independent loads in flight and a row's 8 KB come from one page -- a thread that walks one
-    // path through 253 rows that lie 268 MB apart spends its time in TLB misses (measured: 82 ms instead of 22 at 2^26 paths).
+    // path through 253 rows that lie 268 MB apart is latency-bound (82 ms at 2^26 paths; 37 ms this way, with the row's coefficients in registers).
     constexpr int POL_PPT = 8;
     double acc[3] = {0.0, 0.0, 0.0};  // sum of discounted payoffs, sum of squares, sum of stopping indices
     const int64_t tile_paths = (int64_t)POL_PPT * LSM_NT;
@@ -1959,16 +1959,27 @@ __global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict
         }
         const unsigned mine = alive;
         double df = 1.0;
+        const ST* col = S + t0 + threadIdx.x;
+        ST nxt[POL_PPT];  // row j + 1 is in flight while row j is evaluated: two rows of independent loads per thread
+#pragma unroll
+        for (int q = 0; q < POL_PPT; ++q) nxt[q] = (alive >> q) & 1u ? col[q * LSM_NT] : (ST)0;
         for (int j = 0; j < M; ++j, df *= disc) {
-            if (__syncthreads_and(alive == 0u)) break;  // the whole tile has stopped
-            const ST* row = S + (int64_t)j * ld + t0 + threadIdx.x;
+            if (__all_sync(0xffffffffu, alive == 0u)) break;  // every path of this warp has stopped
             ST buf[POL_PPT];
 #pragma unroll
-            for (int q = 0; q < POL_PPT; ++q) buf[q] = (alive >> q) & 1u ? row[q * LSM_NT] : (ST)0;
+            for (int q = 0; q < POL_PPT; ++q) buf[q] = nxt[q];
+            if (j + 1 < M) {
+                const ST* row = col + (int64_t)(j + 1) * ld;
+#pragma unroll
+                for (int q = 0; q < POL_PPT; ++q) nxt[q] = (alive >> q) & 1u ? row[q * LSM_NT] : (ST)0;
+            }
             const bool last = j == M - 1, normal = __ldg(kind + j) == STEP_NORMAL;
             if (!last && !normal) continue;
             const double* c = tab + (size_t)j * (COEF_LD + 2);
             const double mu = __ldg(c + COEF_LD), is = __ldg(c + COEF_LD + 1);
+            double cj[P + 1];  // the row's coefficients once per row, in registers (one uniform load each instead of one per path)
+#pragma unroll
+            for (int k = 0; k <= P; ++k) cj[k] = __ldg(c + k);
 #pragma unroll
             for (int q = 0; q < POL_PPT; ++q) {
                 if (!((alive >> q) & 1u)) continue;
@@ -1977,8 +1988,9 @@ __global__ void __launch_bounds__(LSM_NT) lsm_policy_kernel(const ST* __restrict
                 bool stop = last;
                 if (!last && pay > 1e-14) {
                     const double x = (s - mu) * is;
-                    double cont = __ldg(c + p);
-                    for (int k = p - 1; k >= 0; --k) cont = fma(cont, x, __ldg(c + k));
+                    double cont = cj[P];
+#pragma unroll
+                    for (int k = P - 1; k >= 0; --k) cont = fma(cont, x, cj[k]);
                     stop = !(pay < cont);
                 }
                 if (stop) { val[q] = df * pay; tau[q] = j; alive &= ~(1u << q); }
@@ -2029,12 +2041,26 @@ extern "C" int mcp_lsm_policy_value(mcp_ctx* ctx, const mcp_pathset* ps, const m
     const double disc = exp(-prm->r * prm->dt);
     double* d_part = (double*)(sb + o_part);
     double* d_fin = (double*)(sb + o_fin);
-    if (ps->dtype == MCP_F32)
-        lsm_policy_kernel<float><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)ps->data, ps->ld, N, M, p, (const double*)(sb + o_tab), (const int*)(sb + o_kind),
-                                                                      prm->strike, prm->is_call, disc, d_part);
-    else
-        lsm_policy_kernel<double><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)ps->data, ps->ld, N, M, p, (const double*)(sb + o_tab), (const int*)(sb + o_kind),
-                                                                       prm->strike, prm->is_call, disc, d_part);
+    {
+        const double* d_tab = (const double*)(sb + o_tab);
+        const int* d_kind = (const int*)(sb + o_kind);
+        auto launch = [&](auto tag) {
+            constexpr int P = decltype(tag)::value;
+            if (ps->dtype == MCP_F32)
+                lsm_policy_kernel<float, P><<<(unsigned)grid, LSM_NT, 0, st>>>((const float*)ps->data, ps->ld, N, M, d_tab, d_kind, prm->strike, prm->is_call, disc, d_part);
+            else
+                lsm_policy_kernel<double, P><<<(unsigned)grid, LSM_NT, 0, st>>>((const double*)ps->data, ps->ld, N, M, d_tab, d_kind, prm->strike, prm->is_call, disc, d_part);
+        };
+        switch (p) {
+            case 0: launch(std::integral_constant<int, 0>{}); break;
+            case 1: launch(std::integral_constant<int, 1>{}); break;
+            case 2: launch(std::integral_constant<int, 2>{}); break;
+            case 3: launch(std::integral_constant<int, 3>{}); break;
+            case 4: launch(std::integral_constant<int, 4>{}); break;
+            case 5: launch(std::integral_constant<int, 5>{}); break;
+            default: launch(std::integral_constant<int, 6>{}); break;
+        }
+    }
     MCP_LAUNCH_CHECK(ctx);
     lsm_reduce_kernel<<<1, 256, 0, st>>>(d_part, (int)grid, 3, d_fin);
     MCP_LAUNCH_CHECK(ctx);
