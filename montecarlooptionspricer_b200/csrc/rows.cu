@@ -21,12 +21,13 @@ struct RowDev {
     double K, r, dt, maturity, disc, sigma, dividend;
 };
 
-// 250 paths per row (PredictionGen.cpp:719) occupy 250 of a CTA's threads whatever its size, and the four pricers are chains of
-// short loops separated by block-wide sums: latency, not throughput.  256-thread CTAs, two per SM (ncu r02a: one 512-thread
-// CTA per SM issued 19 % of the time with 23 % of its stalls at barriers), let one row's barriers hide behind another's work.
-constexpr int ROWS_NT = 256;
+// 250 paths per row (PredictionGen.cpp:719) keep at most 250 threads busy whatever the CTA size, and the four pricers are chains of
+// short loops separated by block-wide sums: latency, not throughput.  Small CTAs, several per SM, let one row's barriers hide
+// behind another row's work: one 512-thread CTA per SM issued 19 % of the time with 23 % of its stalls at barriers (ncu r02a,
+// 70 ms per 16384 rows); two of 256 threads 38 ms; four of 128 threads 27 ms; eight of 64 threads the same 27 ms.
+constexpr int ROWS_NT = 128;
 template <int P>
-__global__ void __launch_bounds__(ROWS_NT, 2) rows_price_kernel(const RowDev* __restrict__ rows, const float* __restrict__ slabs, int64_t ld, int n, int n_br,
+__global__ void __launch_bounds__(ROWS_NT, 4) rows_price_kernel(const RowDev* __restrict__ rows, const float* __restrict__ slabs, int64_t ld, int n, int n_br,
                                                              int max_iter, PhiloxKeys keys, uint64_t path_offset, double* __restrict__ out /*[rows][8]*/) {
     extern __shared__ double sm[];
     __shared__ double res[4];
