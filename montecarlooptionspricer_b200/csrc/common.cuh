@@ -163,4 +163,6 @@ static inline int64_t mcp_round_up(int64_t x, int64_t m) { return (x + m - 1) / 
 
 // batched row generation (gen_rbergomi.cu), used by rows.cu
 int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t model_stride_bytes, const int* n_steps, int n_rows, int n_paths,
-                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld);
+                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld, void* host_stage = nullptr,
+                      void* dev_stage = nullptr, size_t stage_bytes = 0, cudaEvent_t ev_start = nullptr);
+size_t mcp_rows_stage_bytes(int n_rows, int max_steps);

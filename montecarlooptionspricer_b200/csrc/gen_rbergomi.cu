@@ -745,9 +745,22 @@ extern "C" int mcp_gen_rbergomi(mcp_ctx* ctx, mcp_pathset* ps, const mcp_rbergom
 // Batched generation for the row driver (rows.cu): row r = its own model, step count and slab; normals of path i of
 // row r are keyed by (seed, path_offset + r * n_paths + i) -- exactly what mcp_gen_rbergomi produces for that row
 // when called with path_offset + r * n_paths.  One launch for all rows.
+// bytes of staging (pinned host AND device, each) that mcp_rows_generate needs for a batch of n_rows rows of at most max_steps steps
+size_t mcp_rows_stage_bytes(int n_rows, int max_steps) {
+    return (size_t)mcp_round_up((int64_t)((size_t)n_rows * sizeof(RbRow)), 256) + (size_t)n_rows * (size_t)next_pow2(max_steps < 1 ? 1 : max_steps) * 24;
+}
+
+// host_stage / dev_stage (both of mcp_rows_stage_bytes, host one pinned): the row descriptors and tables are built straight into
+// the pinned buffer and copied asynchronously -- the call returns with the copy and the kernel queued, nothing waits, so the
+// caller can build the NEXT batch's tables while this one runs (rows.cu).  Both null: private buffers and a synchronous copy.
+// ev_start (nullable) is recorded right before the first device operation of the batch.
 int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t model_stride_bytes, const int* n_steps, int n_rows, int n_paths,
-                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld) {
-    std::vector<RbRow> rows((size_t)n_rows);
+                      uint64_t seed, uint64_t path_offset, float* slabs, int64_t slab_stride, int64_t ld, void* host_stage, void* dev_stage,
+                      size_t stage_bytes, cudaEvent_t ev_start) {
+    std::vector<RbRow> rows_own;
+    RbRow* rows = nullptr;
+    if (host_stage) rows = (RbRow*)host_stage;
+    else { rows_own.resize((size_t)n_rows); rows = rows_own.data(); }
     int max_Mp = 1, live_rows = 0;
     // pass 1 (serial, trivial): validate, place every row's tables in one staging buffer
     size_t tables_bytes = 0;
@@ -769,7 +782,17 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
         if (Mp > max_Mp) max_Mp = Mp;
         ++live_rows;
     }
-    std::vector<unsigned char> tables(tables_bytes);
+    const size_t rows_bytes = (size_t)n_rows * sizeof(RbRow);
+    const size_t rows_span = (size_t)mcp_round_up((int64_t)rows_bytes, 256);
+    std::vector<unsigned char> tables_own;
+    unsigned char* tables = nullptr;
+    if (host_stage) {
+        if (rows_span + tables_bytes > stage_bytes) return mcp_fail(ctx, MCP_ERR_INVALID, "rows: staging buffer too small");
+        tables = (unsigned char*)host_stage + rows_span;
+    } else {
+        tables_own.resize(tables_bytes);
+        tables = tables_own.data();
+    }
     // pass 2: the tables themselves (a few microseconds per row), split over a handful of host threads for large batches
     auto fill = [&](int r_begin, int r_end) {
         std::vector<float> phis, tw, comp2;
@@ -795,7 +818,7 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
             R.P.path_offset = path_offset + (uint64_t)r * (uint64_t)n_paths;
             R.P.ld_draws = 0;
             R.slab_off = (int64_t)r * slab_stride;
-            unsigned char* o = tables.data() + R.table_off;
+            unsigned char* o = tables + R.table_off;
             memcpy(o, phis.data(), (size_t)Mp * 8);
             memcpy(o + (size_t)Mp * 8, tw.data(), (size_t)Mp * 8);
             memcpy(o + (size_t)Mp * 16, comp2.data(), (size_t)Mp * 4);
@@ -827,20 +850,29 @@ int mcp_rows_generate(mcp_ctx* ctx, const mcp_rbergomi_params* models, size_t mo
             for (auto& th : pool) th.join();
         }
     }
-    if (live_rows == 0) return MCP_OK;
-    const size_t rows_bytes = (size_t)n_rows * sizeof(RbRow);
-    const size_t need = mcp_round_up((int64_t)rows_bytes, 256) + tables.size();
-    MCP_TRY(mcp_scratch_reserve(ctx, need));
-    unsigned char* base = (unsigned char*)ctx->scratch;
-    MCP_CUDA(ctx, mcp_memcpy_async(ctx, base, rows.data(), rows_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, mcp_memcpy_async(ctx, base + mcp_round_up((int64_t)rows_bytes, 256), tables.data(), tables.size(), cudaMemcpyHostToDevice, ctx->stream));
-    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    if (live_rows == 0) {
+        if (ev_start) cudaEventRecord(ev_start, ctx->stream);
+        return MCP_OK;
+    }
+    unsigned char* base = (unsigned char*)dev_stage;
+    if (!base) {
+        MCP_TRY(mcp_scratch_reserve(ctx, rows_span + tables_bytes));
+        base = (unsigned char*)ctx->scratch;
+    }
+    if (ev_start) cudaEventRecord(ev_start, ctx->stream);
+    if (host_stage) {  // one copy: descriptors and tables are contiguous in the pinned buffer
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, base, host_stage, rows_span + tables_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, base, rows, rows_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, base + rows_span, tables, tables_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    }
     const size_t smem = smem_bytes(max_Mp, 32);
     if (smem > 227 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: transform of %d points does not fit", max_Mp);
     MCP_TRY(mcp_kernel_config(ctx, (const void*)rbergomi_rows_kernel, NT, smem, nullptr));
     const PhiloxKeys K = philox_make_keys(seed);
     const dim3 grid((unsigned)((n_paths + 31) / 32), (unsigned)n_rows);
-    rbergomi_rows_kernel<<<grid, NT, smem, ctx->stream>>>((const RbRow*)base, K, base + mcp_round_up((int64_t)rows_bytes, 256), slabs);
+    rbergomi_rows_kernel<<<grid, NT, smem, ctx->stream>>>((const RbRow*)base, K, base + rows_span, slabs);
     MCP_LAUNCH_CHECK(ctx);
     return MCP_OK;
 }

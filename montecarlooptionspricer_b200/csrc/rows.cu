@@ -6,6 +6,7 @@
 //                             (small_bodies.cuh -- the same device routines the per-row API uses for small path sets)
 // Rows are independent: a multi-GPU run gives each rank a slice of the rows, no collective.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -105,33 +106,57 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
     }
     const int64_t ld = mcp_round_up(n_paths, 128);
     const int64_t slab_stride = (int64_t)(max_steps + 1) * ld;
-    // rows per chunk: at most ~2 GiB of slabs at a time
-    int64_t chunk = ((int64_t)2 << 30) / (slab_stride * 4);
+    // Rows go through in chunks, TWO IN FLIGHT: while the device generates and prices chunk c, the host builds the transform
+    // tables of chunk c + 1 straight into pinned memory (one asynchronous copy per chunk; the pageable, synchronous copy of the
+    // first version cost more than the generation kernel).  Every per-chunk buffer exists twice (parity of the chunk index);
+    // nothing in the loop waits for the device except the hand-over of a chunk's results, one chunk late.
+    int64_t chunk = ((int64_t)2 << 30) / (slab_stride * 4);  // at most ~2 GiB of slabs per chunk (two chunks are resident)
+    {
+        // rows per chunk: measured at 16384 rows, 2048 / 4096 / 8192 / 16384 rows per chunk -> 44.2 / 40.0 / 38.5 / 38.3 ms (many CTA
+        // waves per launch keep the tail of the pricing kernel small); MCP_ROWS_CHUNK overrides
+        const char* ce = getenv("MCP_ROWS_CHUNK");
+        const int64_t cap = ce && *ce ? atoll(ce) : 8192;
+        if (cap >= 1 && chunk > cap) chunk = cap;
+    }
     if (chunk < 1) chunk = 1;
     if (chunk > n_rows) chunk = n_rows;
     const size_t smem = (4 * (size_t)n_paths + (size_t)(max_steps + 1) * 2 + 8) * sizeof(double);
     if (smem > 200 * 1024) return mcp_fail(ctx, MCP_ERR_UNSUPPORTED, "rows: %d paths x %d steps does not fit one CTA", n_paths, max_steps);
     RowsFn fn = pick_rows(poly_order);
     MCP_TRY(mcp_kernel_config(ctx, (const void*)fn, ROWS_NT, smem, nullptr));
-    MCP_TRY(mcp_carry_reserve(ctx, (size_t)chunk * slab_stride * 4 + (size_t)chunk * (sizeof(RowDev) + 64) + 4096));
-    float* d_slabs = (float*)ctx->carry;
-    RowDev* d_rows = (RowDev*)((unsigned char*)ctx->carry + (size_t)chunk * slab_stride * 4);
-    double* d_out = (double*)((unsigned char*)d_rows + mcp_round_up((int64_t)(chunk * sizeof(RowDev)), 256));
+    const size_t slab_bytes = (size_t)chunk * slab_stride * 4;
+    const size_t rowdev_bytes = (size_t)mcp_round_up((int64_t)(chunk * sizeof(RowDev)), 256), out_bytes = (size_t)mcp_round_up(chunk * 8 * 8, 256);
+    const size_t stage_bytes = (size_t)mcp_round_up((int64_t)mcp_rows_stage_bytes((int)chunk, max_steps), 256);
+    MCP_TRY(mcp_carry_reserve(ctx, 2 * (slab_bytes + rowdev_bytes + out_bytes) + 4096));
+    MCP_TRY(mcp_scratch_reserve(ctx, 2 * stage_bytes));
+    MCP_TRY(mcp_pinned_reserve(ctx, 2 * (stage_bytes + rowdev_bytes + out_bytes)));
+    struct Slot {
+        float* d_slabs; RowDev* d_rows; double* d_out; unsigned char* d_stage;
+        unsigned char* h_stage; RowDev* h_rows; double* h_out;
+        cudaEvent_t e0, e1, e2, done;
+        int64_t r0; int nr;
+    } slot[2];
+    for (int b = 0; b < 2; ++b) {
+        unsigned char* dc = (unsigned char*)ctx->carry + (size_t)b * (slab_bytes + rowdev_bytes + out_bytes);
+        slot[b].d_slabs = (float*)dc; slot[b].d_rows = (RowDev*)(dc + slab_bytes); slot[b].d_out = (double*)(dc + slab_bytes + rowdev_bytes);
+        slot[b].d_stage = (unsigned char*)ctx->scratch + (size_t)b * stage_bytes;
+        unsigned char* hp = (unsigned char*)ctx->pinned + (size_t)b * (stage_bytes + rowdev_bytes + out_bytes);
+        slot[b].h_stage = hp; slot[b].h_rows = (RowDev*)(hp + stage_bytes); slot[b].h_out = (double*)(hp + stage_bytes + rowdev_bytes);
+        slot[b].e0 = mcp_prof_event(ctx, 4080 + 4 * (size_t)b); slot[b].e1 = mcp_prof_event(ctx, 4081 + 4 * (size_t)b);
+        slot[b].e2 = mcp_prof_event(ctx, 4082 + 4 * (size_t)b); slot[b].done = mcp_prof_event(ctx, 4083 + 4 * (size_t)b);
+        if (!slot[b].e0 || !slot[b].e1 || !slot[b].e2 || !slot[b].done) return mcp_fail(ctx, MCP_ERR_CUDA, "cudaEventCreate failed");
+        slot[b].r0 = 0; slot[b].nr = 0;
+    }
     const PhiloxKeys keys = philox_make_keys(seed ^ 0x5bd1e995ull);  // resampling stream of the Branching pricer
-    cudaEvent_t e0, e1, e2;
-    MCP_CUDA(ctx, cudaEventCreate(&e0));
-    MCP_CUDA(ctx, cudaEventCreate(&e1));
-    MCP_CUDA(ctx, cudaEventCreate(&e2));
     float g_total = 0.f, p_total = 0.f;
     int rc = MCP_OK;
-    std::vector<RowDev> h_rows((size_t)chunk);
     std::vector<int> steps((size_t)chunk);
-    std::vector<double> h_out((size_t)chunk * 8);
-    for (int64_t r0 = 0; r0 < n_rows && rc == MCP_OK; r0 += chunk) {
-        const int nr = (int)(n_rows - r0 < chunk ? n_rows - r0 : chunk);
+
+    auto issue = [&](Slot& s, int64_t r0, int nr) -> int {
+        s.r0 = r0; s.nr = nr;
         for (int k = 0; k < nr; ++k) {
             const mcp_row& R = rows[r0 + k];
-            RowDev& D = h_rows[(size_t)k];
+            RowDev& D = s.h_rows[k];
             D.slab_off = (int64_t)k * slab_stride;
             // a degenerate model (H < 0, |rho| > 1, xi < 0, NaN ...) spoils only its own row: no paths, NaN results (see mcp_rows_generate)
             const bool degenerate = !(R.model.dt > 0.0) || !(R.model.H >= 0.0) || !(fabs(R.model.rho) <= 1.0) || !(R.model.xi >= 0.0);
@@ -141,39 +166,51 @@ extern "C" int mcp_price_rows(mcp_ctx* ctx, const mcp_row* rows, int n_rows, int
             D.disc = exp(-R.r * R.dt);
             steps[(size_t)k] = D.n_steps;
         }
-        cudaEventRecord(e0, ctx->stream);
-        rc = mcp_rows_generate(ctx, &rows[r0].model, sizeof(mcp_row), steps.data(), nr, n_paths, seed, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_slabs,
-                               slab_stride, ld);
-        if (rc != MCP_OK) break;
-        cudaEventRecord(e1, ctx->stream);
-        if (mcp_memcpy_async(ctx, d_rows, h_rows.data(), (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: H2D failed"); break; }
-        fn<<<nr, ROWS_NT, smem, ctx->stream>>>(d_rows, d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, d_out);
-        ctx->launches++;
-        cudaEventRecord(e2, ctx->stream);
-        if (mcp_memcpy_async(ctx, h_out.data(), d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-            rc = mcp_fail(ctx, MCP_ERR_CUDA, "rows: pricing kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-            break;
-        }
-        for (int k = 0; k < nr; ++k) {
-            mcp_row_result& o = out[r0 + k];
-            o.asymptotic = h_out[(size_t)k * 8 + 0];
-            o.branching = h_out[(size_t)k * 8 + 1];
-            o.lsm = h_out[(size_t)k * 8 + 2];
-            o.martingale = h_out[(size_t)k * 8 + 3];
-            o.lsm_std_error = h_out[(size_t)k * 8 + 4];
-            if (h_rows[(size_t)k].n_steps != rows[r0 + k].n_steps) {  // degenerate model: what the reference's NaN paths give
+        MCP_TRY(mcp_rows_generate(ctx, &rows[r0].model, sizeof(mcp_row), steps.data(), nr, n_paths, seed, path_offset + (uint64_t)r0 * (uint64_t)n_paths, s.d_slabs,
+                                  slab_stride, ld, s.h_stage, s.d_stage, stage_bytes, s.e0));
+        MCP_CUDA(ctx, cudaEventRecord(s.e1, ctx->stream));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, s.d_rows, s.h_rows, (size_t)nr * sizeof(RowDev), cudaMemcpyHostToDevice, ctx->stream));
+        fn<<<nr, ROWS_NT, smem, ctx->stream>>>(s.d_rows, s.d_slabs, ld, n_paths, num_branches, max_iterations, keys, path_offset + (uint64_t)r0 * (uint64_t)n_paths, s.d_out);
+        MCP_LAUNCH_CHECK(ctx);
+        MCP_CUDA(ctx, cudaEventRecord(s.e2, ctx->stream));
+        MCP_CUDA(ctx, mcp_memcpy_async(ctx, s.h_out, s.d_out, (size_t)nr * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaEventRecord(s.done, ctx->stream));
+        return MCP_OK;
+    };
+    auto finish = [&](Slot& s) -> int {
+        if (s.nr == 0) return MCP_OK;
+        if (cudaEventSynchronize(s.done) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+            return mcp_fail(ctx, MCP_ERR_CUDA, "rows: pricing kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        for (int k = 0; k < s.nr; ++k) {
+            mcp_row_result& o = out[s.r0 + k];
+            o.asymptotic = s.h_out[(size_t)k * 8 + 0];
+            o.branching = s.h_out[(size_t)k * 8 + 1];
+            o.lsm = s.h_out[(size_t)k * 8 + 2];
+            o.martingale = s.h_out[(size_t)k * 8 + 3];
+            o.lsm_std_error = s.h_out[(size_t)k * 8 + 4];
+            if (s.h_rows[k].n_steps != rows[s.r0 + k].n_steps) {  // degenerate model: what the reference's NaN paths give
                 const double qnan = nan("");
                 o.asymptotic = o.branching = o.lsm = o.martingale = o.lsm_std_error = qnan;
             }
         }
         float a = 0.f, b = 0.f;
-        if (cudaEventElapsedTime(&a, e0, e1) == cudaSuccess) g_total += a;
-        if (cudaEventElapsedTime(&b, e1, e2) == cudaSuccess) p_total += b;
+        if (cudaEventElapsedTime(&a, s.e0, s.e1) == cudaSuccess) g_total += a;
+        if (cudaEventElapsedTime(&b, s.e1, s.e2) == cudaSuccess) p_total += b;
+        s.nr = 0;
+        return MCP_OK;
+    };
+    int c = 0;
+    for (int64_t r0 = 0; r0 < n_rows && rc == MCP_OK; r0 += chunk, ++c) {
+        const int nr = (int)(n_rows - r0 < chunk ? n_rows - r0 : chunk);
+        Slot& s = slot[c & 1];
+        rc = finish(s);                      // the chunk that used this slot two issues ago
+        if (rc == MCP_OK) rc = issue(s, r0, nr);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
+    for (int b = 0; b < 2; ++b) {
+        const int r2 = finish(slot[(c + b) & 1]);  // oldest first
+        if (rc == MCP_OK) rc = r2;
+    }
+    if (rc != MCP_OK) cudaStreamSynchronize(ctx->stream);
     if (gen_ms) *gen_ms = g_total;
     if (price_ms) *price_ms = p_total;
     return rc;
